@@ -1,0 +1,924 @@
+// api.cu -- C-ABI of libcadrays_b200.so (include/cadrays_b200.h) and the host
+// orchestration of the wavefront path tracer.  The reference call site each entry
+// point replaces is cited in the header.
+#include "../../include/cadrays_b200.h"
+#include "host_scene.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace crt;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg)
+{
+  g_error = msg;
+  return code;
+}
+
+#define CRT_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      cudaGetLastError();                                                                       \
+      return fail(e_ == cudaErrorMemoryAllocation ? CRT_ERR_OUT_OF_MEMORY : CRT_ERR_CUDA,       \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+    }                                                                                           \
+  } while (0)
+
+#define CRT_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) return fail(CRT_ERR_INVALID_ARG, msg);         \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count)
+  {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+enum Family { F_GENERATE = 0, F_EXTEND, F_SHADE, F_CONNECT, F_RESOLVE, F_RENDER, F_COUNT };
+
+struct TimedSpan { int family; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct crt_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+
+  // host scene (what CADRays hands to OCCT)
+  HostScene scene;
+  bool geometry_dirty = true;
+  std::vector<uint8_t> blob;
+  bool has_layout = false;
+  std::vector<crt_bsdf> mats;
+  std::vector<float> lights;         // 8 floats per light, shader form
+  std::vector<float> env;            // rgba per texel
+  uint32_t env_w = 0, env_h = 0;
+  bool mats_dirty = true, lights_dirty = true, env_dirty = true;
+  crt_params params;
+  crt_camera cam;
+  uint32_t width = 0, height = 0;
+
+  // device scene
+  DevBuf<float4> d_nodes, d_tri_verts, d_tri_nrm, d_inst, d_mats, d_lights, d_env;
+  DeviceScene ds{};
+  DeviceParams dp{};
+
+  // path state
+  DevBuf<float4> ray_o, ray_d, thr, rad, hit, sh_o, sh_d, sh_c;
+  DevBuf<int32_t> hit_inst;
+  DevBuf<uint32_t> queue0, queue1, counters, seeds;
+  uint32_t state_capacity = 0;       // path slots allocated
+  uint32_t batch = 0;                // samples per pixel in flight
+  std::vector<uint32_t> h_seeds;
+
+  // accumulation
+  DevBuf<float4> accum_internal;
+  float4* accum = nullptr;
+  bool accum_external = false;
+  uint64_t first_sample = 0, next_sample = 0;
+  uint32_t rng_hi = 0, rng_lo = 0; uint64_t rng_index = 0; bool rng_valid = false;
+
+  // read-back staging
+  DevBuf<uint8_t> d_ldr;
+  DevBuf<float> d_hdr;
+
+  // metrics
+  DevBuf<Counters> d_counters;
+  bool stats_on = false;
+  bool timing_on = false;
+  std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double family_ms[F_COUNT] = {};
+  uint64_t family_launches[F_COUNT] = {};
+};
+
+namespace {
+
+int set_device(crt_context* c)
+{
+  if (c->device < 0) return fail(CRT_ERR_NO_DEVICE, "host-only context: no CUDA device bound (there is no CPU fallback)");
+  CRT_CUDA(cudaSetDevice(c->device));
+  return CRT_OK;
+}
+
+// math_BullardGenerator: seed of sample index k = k-th NextInt() >> 2.
+uint32_t frame_seed(crt_context* c, uint64_t index)
+{
+  if (!c->rng_valid || index < c->rng_index) {
+    c->rng_hi = c->params.frame_seed0;
+    c->rng_lo = c->params.frame_seed0 ^ 0x49616E42u;
+    c->rng_index = 0;
+    c->rng_valid = true;
+  }
+  uint32_t out = 0;
+  // state after producing sample (rng_index - 1); step until `index` is produced
+  while (c->rng_index <= index) {
+    c->rng_hi = (c->rng_hi >> 2) + (c->rng_hi << 2);
+    c->rng_hi += c->rng_lo;
+    c->rng_lo += c->rng_hi;
+    out = c->rng_hi;
+    c->rng_index++;
+  }
+  return out >> 2;
+}
+
+cudaEvent_t get_event(crt_context* c)
+{
+  if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct SpanGuard {
+  crt_context* c; int family; cudaEvent_t a = nullptr;
+  SpanGuard(crt_context* c_, int f) : c(c_), family(f)
+  {
+    if (c->timing_on) { a = get_event(c); cudaEventRecord(a, c->stream); }
+  }
+  ~SpanGuard()
+  {
+    if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({ family, a, b }); }
+  }
+};
+
+void reset_accum_state(crt_context* c)
+{
+  c->next_sample = c->first_sample;
+  if (c->device >= 0 && c->accum && c->width && c->height)
+    cudaMemsetAsync(c->accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream);
+}
+
+// camera basis and light table: same formulas as the oracle's orc_set_camera /
+// orc_set_lights (host libm tanf/cosf on both sides)
+void update_device_params(crt_context* c)
+{
+  DeviceParams& P = c->dp;
+  const crt_params& p = c->params;
+  P.max_depth = std::max(1, std::min(p.max_depth, 64));
+  P.max_radiance = p.max_radiance;
+  P.two_sided = p.two_sided;
+  P.rng_radius = p.coherent_rng ? 8u : 1u;
+  P.aperture_radius = p.aperture_radius;
+  P.focal_dist = p.focal_dist;
+  P.env_as_background = (p.env_as_background && c->env_w) ? 1 : 0;
+  P.russian_roulette = p.russian_roulette;
+  for (int k = 0; k < 3; ++k) P.background[k] = p.background[k];
+  const crt_camera& cam = c->cam;
+  v3 w = normalize3(V(cam.dir[0], cam.dir[1], cam.dir[2]));
+  v3 u = normalize3(cross3(w, V(cam.up[0], cam.up[1], cam.up[2])));
+  v3 v = cross3(u, w);
+  P.cu[0] = u.x; P.cu[1] = u.y; P.cu[2] = u.z;
+  P.cv[0] = v.x; P.cv[1] = v.y; P.cv[2] = v.z;
+  P.cw[0] = w.x; P.cw[1] = w.y; P.cw[2] = w.z;
+  for (int k = 0; k < 3; ++k) P.eye[k] = cam.eye[k];
+  P.hh = cam.is_ortho ? cam.ortho_scale * 0.5f : tanf(cam.fovy_deg * 0.5f * 0.0174532925199433f);
+  P.hw = P.hh * cam.aspect;
+  P.is_ortho = cam.is_ortho;
+  P.width = c->width; P.height = c->height;
+  P.tiles_x = (c->width + 7u) / 8u;
+  P.tiles_y = (c->height + 3u) / 4u;
+}
+
+int ensure_path_state(crt_context* c, uint32_t batch)
+{
+  const uint64_t per_sample = (uint64_t)c->dp.tiles_x * c->dp.tiles_y * 32u;
+  const uint64_t need = per_sample * batch;
+  if (need > 0x7fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
+  if (need <= c->state_capacity) return CRT_OK;
+  const size_t n = (size_t)need;
+  CRT_CUDA(c->ray_o.ensure(n)); CRT_CUDA(c->ray_d.ensure(n)); CRT_CUDA(c->thr.ensure(n));
+  CRT_CUDA(c->rad.ensure(n)); CRT_CUDA(c->hit.ensure(n)); CRT_CUDA(c->hit_inst.ensure(n));
+  CRT_CUDA(c->queue0.ensure(n)); CRT_CUDA(c->queue1.ensure(n));
+  CRT_CUDA(c->sh_o.ensure(n)); CRT_CUDA(c->sh_d.ensure(n)); CRT_CUDA(c->sh_c.ensure(n));
+  c->state_capacity = (uint32_t)need;
+  return CRT_OK;
+}
+
+uint32_t auto_batch(const crt_context* c)
+{
+  if (c->params.samples_per_batch > 0) return (uint32_t)c->params.samples_per_batch;
+  const uint64_t px = (uint64_t)c->width * c->height;
+  if (!px) return 1;
+  uint64_t b = (8ull << 20) / px;   // about 8 M paths in flight
+  return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b, 64));
+}
+
+int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
+{
+  CRT_CUDA(c->d_nodes.ensure(std::max<size_t>(L.nodes.size(), 4)));
+  CRT_CUDA(c->d_tri_verts.ensure(std::max<size_t>(L.tri_verts.size(), 3)));
+  CRT_CUDA(c->d_tri_nrm.ensure(std::max<size_t>(L.tri_nrm.size(), 3)));
+  CRT_CUDA(c->d_inst.ensure(std::max<size_t>(L.inst.size(), 4)));
+  if (!L.nodes.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_nodes.p, L.nodes.data(), L.nodes.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.tri_verts.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_verts.p, L.tri_verts.data(), L.tri_verts.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.tri_nrm.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_nrm.p, L.tri_nrm.data(), L.tri_nrm.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.inst.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_inst.p, L.inst.data(), L.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  c->ds.nodes = c->d_nodes.p; c->ds.tri_verts = c->d_tri_verts.p; c->ds.tri_nrm = c->d_tri_nrm.p; c->ds.inst = c->d_inst.p;
+  c->ds.top_root = L.top_root;
+  c->ds.scene_eps = scene_eps;
+  if (L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
+    return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
+  c->has_layout = true;
+  return CRT_OK;
+}
+
+int load_blob(crt_context* c)
+{
+  BlobView view;
+  std::string err;
+  if (!parse_blob(c->blob.data(), c->blob.size(), view, err)) return fail(CRT_ERR_FORMAT, err);
+  DeviceLayout L;
+  if (!build_device_layout(view, L, err)) return fail(CRT_ERR_FORMAT, err);
+  return upload_layout(c, L, view.hdr.scene_eps);
+}
+
+int upload_tables(crt_context* c)
+{
+  if (c->mats_dirty) {
+    CRT_CUDA(c->d_mats.ensure(std::max<size_t>(c->mats.size() * 8, 8)));
+    if (!c->mats.empty())
+      CRT_CUDA(cudaMemcpyAsync(c->d_mats.p, c->mats.data(), c->mats.size() * sizeof(crt_bsdf), cudaMemcpyHostToDevice, c->stream));
+    c->ds.mats = c->d_mats.p; c->ds.n_mats = (uint32_t)c->mats.size();
+    c->mats_dirty = false;
+  }
+  if (c->lights_dirty) {
+    CRT_CUDA(c->d_lights.ensure(std::max<size_t>(c->lights.size() / 4, 2)));
+    if (!c->lights.empty())
+      CRT_CUDA(cudaMemcpyAsync(c->d_lights.p, c->lights.data(), c->lights.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    c->ds.lights = c->d_lights.p; c->ds.n_lights = (uint32_t)(c->lights.size() / 8);
+    c->lights_dirty = false;
+  }
+  if (c->env_dirty) {
+    CRT_CUDA(c->d_env.ensure(std::max<size_t>(c->env.size() / 4, 1)));
+    if (!c->env.empty())
+      CRT_CUDA(cudaMemcpyAsync(c->d_env.p, c->env.data(), c->env.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    c->ds.env = c->d_env.p; c->ds.env_w = c->env_w; c->ds.env_h = c->env_h;
+    c->env_dirty = false;
+  }
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  return CRT_OK;
+}
+
+int grid_for(const crt_context* c, int blocks_per_sm) { return c->sm_count * blocks_per_sm; }
+
+template <bool COUNT>
+int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
+{
+  PathState st;
+  st.ray_o = c->ray_o.p; st.ray_d = c->ray_d.p; st.thr = c->thr.p; st.rad = c->rad.p;
+  st.hit = c->hit.p; st.hit_inst = c->hit_inst.p;
+  st.queue[0] = c->queue0.p; st.queue[1] = c->queue1.p;
+  st.sh_o = c->sh_o.p; st.sh_d = c->sh_d.p; st.sh_c = c->sh_c.p;
+  const int depth_max = c->dp.max_depth;
+  st.n_active = c->counters.p;
+  st.n_shadow = c->counters.p + (depth_max + 1);
+  Counters* gc = c->d_counters.p;
+  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (2 * depth_max + 2), c->stream));
+  {
+    SpanGuard g(c, F_GENERATE);
+    k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
+  }
+  for (int depth = 0; depth < depth_max; ++depth) {
+    {
+      SpanGuard g(c, F_EXTEND);
+      k_extend<COUNT><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+    }
+    {
+      SpanGuard g(c, F_SHADE);
+      k_shade<COUNT><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
+    }
+    {
+      SpanGuard g(c, F_CONNECT);
+      k_connect<COUNT><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+    }
+  }
+  {
+    SpanGuard g(c, F_RESOLVE);
+    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
+  }
+  CRT_CUDA(cudaGetLastError());
+  return CRT_OK;
+}
+
+int render_impl(crt_context* c, uint32_t n_samples)
+{
+  if (!c->has_layout || c->geometry_dirty) return fail(CRT_ERR_STATE, "crt_render before crt_commit");
+  if (!c->width || !c->height) return fail(CRT_ERR_STATE, "crt_render before crt_resize");
+  if (!c->accum) return fail(CRT_ERR_STATE, "no accumulation buffer");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = upload_tables(c))) return rc;
+  update_device_params(c);
+  if (n_samples == 0) return CRT_OK;
+  const uint32_t batch = std::min(auto_batch(c), n_samples);
+  if ((rc = ensure_path_state(c, batch))) return rc;
+  CRT_CUDA(c->counters.ensure(2 * 64 + 4));
+  CRT_CUDA(c->seeds.ensure(n_samples));
+  c->h_seeds.resize(n_samples);
+  for (uint32_t k = 0; k < n_samples; ++k) c->h_seeds[k] = frame_seed(c, c->next_sample + k);
+  CRT_CUDA(cudaMemcpyAsync(c->seeds.p, c->h_seeds.data(), sizeof(uint32_t) * n_samples, cudaMemcpyHostToDevice, c->stream));
+  SpanGuard whole(c, F_RENDER);
+  for (uint32_t done = 0; done < n_samples; done += batch) {
+    const uint32_t nb = std::min(batch, n_samples - done);
+    rc = c->stats_on ? launch_batch<true>(c, nb, c->seeds.p + done) : launch_batch<false>(c, nb, c->seeds.p + done);
+    if (rc) return rc;
+  }
+  c->next_sample += n_samples;
+  return CRT_OK;
+}
+
+void collect_spans(crt_context* c)
+{
+  for (TimedSpan& s : c->spans) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      c->family_ms[s.family] += ms;
+      c->family_launches[s.family] += 1;
+    }
+    c->event_pool.push_back(s.a);
+    c->event_pool.push_back(s.b);
+  }
+  c->spans.clear();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+const char* crt_last_error(void) { return g_error.c_str(); }
+int crt_abi_version(void) { return CRT_ABI_VERSION; }
+
+int crt_params_default(crt_params* p)
+{
+  CRT_REQUIRE(p, "null params");
+  std::memset(p, 0, sizeof *p);
+  p->max_depth = 8;             // CADRays' GI slider spans 1..32 (SettingsWidget.cxx:310-316)
+  p->max_radiance = 50.0f;      // OCCT default RadianceClampingValue (SURVEY 5.6 range 1..1000)
+  p->two_sided = 0;
+  p->coherent_rng = 0;
+  p->aperture_radius = 0.0f;
+  p->focal_dist = 1.0f;
+  p->tone_map = 0;
+  p->white_point = 1.0f;
+  p->exposure = 0.0f;
+  p->env_as_background = 1;
+  p->frame_seed0 = 1;
+  p->russian_roulette = 1;
+  p->samples_per_batch = 0;
+  return CRT_OK;
+}
+
+int crt_create(int device_ordinal, crt_context** out)
+{
+  CRT_REQUIRE(out, "null out_ctx");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(CRT_ERR_NO_DEVICE, "no CUDA device available (libcadrays_b200 has no CPU fallback)");
+  }
+  if (device_ordinal < 0 || device_ordinal >= count) return fail(CRT_ERR_INVALID_ARG, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CRT_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major != 10)
+    return fail(CRT_ERR_NO_DEVICE, "device is not sm_100-class; this library carries sm_100a code only");
+  crt_context* c = new (std::nothrow) crt_context();
+  if (!c) return fail(CRT_ERR_OUT_OF_MEMORY, "host allocation failed");
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  crt_params_default(&c->params);
+  std::memset(&c->cam, 0, sizeof c->cam);
+  c->cam.dir[1] = 1.0f; c->cam.up[2] = 1.0f; c->cam.fovy_deg = 45.0f; c->cam.aspect = 1.0f; c->cam.ortho_scale = 1.0f;
+  cudaError_t se = cudaSetDevice(device_ordinal);
+  if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (se == cudaSuccess) se = c->d_counters.ensure(1);
+  if (se == cudaSuccess) se = cudaMemset(c->d_counters.p, 0, sizeof(Counters));
+  if (se != cudaSuccess) {
+    std::string m = std::string("context setup: ") + cudaGetErrorString(se);
+    delete c;
+    return fail(CRT_ERR_CUDA, m);
+  }
+  *out = c;
+  return CRT_OK;
+}
+
+int crt_create_host_only(crt_context** out)
+{
+  CRT_REQUIRE(out, "null out_ctx");
+  crt_context* c = new (std::nothrow) crt_context();
+  if (!c) return fail(CRT_ERR_OUT_OF_MEMORY, "host allocation failed");
+  c->device = -1;
+  crt_params_default(&c->params);
+  std::memset(&c->cam, 0, sizeof c->cam);
+  *out = c;
+  return CRT_OK;
+}
+
+void crt_destroy(crt_context* c)
+{
+  if (!c) return;
+  if (c->device < 0) { delete c; return; }
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  collect_spans(c);
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  c->d_nodes.release(); c->d_tri_verts.release(); c->d_tri_nrm.release(); c->d_inst.release();
+  c->d_mats.release(); c->d_lights.release(); c->d_env.release();
+  c->ray_o.release(); c->ray_d.release(); c->thr.release(); c->rad.release(); c->hit.release();
+  c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();
+  c->queue0.release(); c->queue1.release(); c->counters.release(); c->seeds.release();
+  c->accum_internal.release(); c->d_ldr.release(); c->d_hdr.release(); c->d_counters.release();
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int crt_mesh_create(crt_context* c, const float* pos, const float* nrm, const float* uv,
+                    uint32_t n_verts, const uint32_t* idx, uint32_t n_tris, uint32_t* out_id)
+{
+  CRT_REQUIRE(c && pos && idx && out_id, "null argument");
+  CRT_REQUIRE(n_verts > 0 && n_tris > 0, "empty mesh");
+  for (size_t i = 0; i < (size_t)3 * n_tris; ++i)
+    if (idx[i] >= n_verts) return fail(CRT_ERR_INVALID_ARG, "triangle index out of range");
+  for (size_t i = 0; i < (size_t)3 * n_verts; ++i)
+    if (!std::isfinite(pos[i])) return fail(CRT_ERR_INVALID_ARG, "non-finite vertex position");
+  Mesh m;
+  m.pos.assign(pos, pos + (size_t)3 * n_verts);
+  m.idx.assign(idx, idx + (size_t)3 * n_tris);
+  if (nrm) {
+    m.nrm.assign(nrm, nrm + (size_t)3 * n_verts);
+  } else {
+    // area-weighted vertex normals from the faces (Assimp's aiProcess_GenNormals stands in
+    // for this on the reference side, MeshImporter.cxx:73-106)
+    std::vector<double> acc((size_t)3 * n_verts, 0.0);
+    for (uint32_t t = 0; t < n_tris; ++t) {
+      const float* a = &pos[3 * (size_t)idx[3 * t]];
+      const float* b = &pos[3 * (size_t)idx[3 * t + 1]];
+      const float* d = &pos[3 * (size_t)idx[3 * t + 2]];
+      double e0[3] = { (double)b[0] - a[0], (double)b[1] - a[1], (double)b[2] - a[2] };
+      double e1[3] = { (double)d[0] - a[0], (double)d[1] - a[1], (double)d[2] - a[2] };
+      double n[3] = { e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0] };
+      for (int k = 0; k < 3; ++k)
+        for (int q = 0; q < 3; ++q) acc[3 * (size_t)idx[3 * t + k] + q] += n[q];
+    }
+    m.nrm.resize((size_t)3 * n_verts);
+    for (uint32_t v = 0; v < n_verts; ++v) {
+      double l = std::sqrt(acc[3 * v] * acc[3 * v] + acc[3 * v + 1] * acc[3 * v + 1] + acc[3 * v + 2] * acc[3 * v + 2]);
+      if (l > 0.0) { for (int q = 0; q < 3; ++q) m.nrm[3 * (size_t)v + q] = (float)(acc[3 * v + q] / l); }
+      else { m.nrm[3 * (size_t)v] = 0.0f; m.nrm[3 * (size_t)v + 1] = 0.0f; m.nrm[3 * (size_t)v + 2] = 1.0f; }
+    }
+  }
+  if (uv) { m.uv.assign(uv, uv + (size_t)2 * n_verts); m.has_uv = true; }
+  else m.uv.assign((size_t)2 * n_verts, 0.0f);
+  c->scene.meshes.push_back(std::move(m));
+  *out_id = (uint32_t)c->scene.meshes.size() - 1;
+  return CRT_OK;
+}
+
+static const float k_identity[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+
+int crt_instance_add(crt_context* c, uint32_t mesh_id, const float xf[12], uint32_t material_id, uint32_t* out_id)
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_REQUIRE(mesh_id < c->scene.meshes.size(), "unknown mesh id");
+  Instance in;
+  in.mesh = mesh_id; in.material = material_id;
+  std::memcpy(in.xf, xf ? xf : k_identity, sizeof in.xf);
+  for (int k = 0; k < 12; ++k) if (!std::isfinite(in.xf[k])) return fail(CRT_ERR_INVALID_ARG, "non-finite transform");
+  c->scene.instances.push_back(in);
+  c->geometry_dirty = true;
+  if (out_id) *out_id = (uint32_t)c->scene.instances.size() - 1;
+  return CRT_OK;
+}
+
+int crt_instance_set_transform(crt_context* c, uint32_t inst, const float xf[12])
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_REQUIRE(inst < c->scene.instances.size(), "unknown instance id");
+  std::memcpy(c->scene.instances[inst].xf, xf ? xf : k_identity, sizeof(float) * 12);
+  c->geometry_dirty = true;
+  return CRT_OK;
+}
+
+int crt_instance_set_material(crt_context* c, uint32_t inst, uint32_t material_id)
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_REQUIRE(inst < c->scene.instances.size(), "unknown instance id");
+  c->scene.instances[inst].material = material_id;
+  c->geometry_dirty = true;
+  return CRT_OK;
+}
+
+int crt_scene_clear(crt_context* c)
+{
+  CRT_REQUIRE(c, "null context");
+  c->scene.meshes.clear();
+  c->scene.instances.clear();
+  c->geometry_dirty = true;
+  return CRT_OK;
+}
+
+int crt_materials_set(crt_context* c, const crt_bsdf* b, uint32_t n)
+{
+  CRT_REQUIRE(c && (b || n == 0), "null argument");
+  c->mats.assign(b, b + n);
+  c->mats_dirty = true;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_lights_set(crt_context* c, const crt_light* l, uint32_t n)
+{
+  CRT_REQUIRE(c && (l || n == 0), "null argument");
+  c->lights.assign((size_t)8 * n, 0.0f);
+  for (uint32_t i = 0; i < n; ++i) {
+    float* r = &c->lights[8 * (size_t)i];
+    r[0] = l[i].emission[0]; r[1] = l[i].emission[1]; r[2] = l[i].emission[2];
+    if (l[i].is_point) {
+      r[3] = l[i].smoothness;
+      r[4] = l[i].posdir[0]; r[5] = l[i].posdir[1]; r[6] = l[i].posdir[2]; r[7] = 1.0f;
+    } else {
+      r[3] = cosf(l[i].smoothness);
+      v3 d = normalize3(V(l[i].posdir[0], l[i].posdir[1], l[i].posdir[2]));
+      r[4] = -d.x; r[5] = -d.y; r[6] = -d.z; r[7] = 0.0f;
+    }
+  }
+  c->lights_dirty = true;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_envmap_set_rgb32f(crt_context* c, const float* rgb, uint32_t w, uint32_t h)
+{
+  CRT_REQUIRE(c, "null context");
+  if (!rgb || !w || !h) { c->env.clear(); c->env_w = c->env_h = 0; }
+  else {
+    c->env.resize((size_t)4 * w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+      c->env[4 * i] = rgb[3 * i]; c->env[4 * i + 1] = rgb[3 * i + 1]; c->env[4 * i + 2] = rgb[3 * i + 2]; c->env[4 * i + 3] = 0.0f;
+    }
+    c->env_w = w; c->env_h = h;
+  }
+  c->env_dirty = true;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_envmap_set_rgb8(crt_context* c, const uint8_t* rgb, uint32_t w, uint32_t h)
+{
+  CRT_REQUIRE(c, "null context");
+  if (!rgb || !w || !h) return crt_envmap_set_rgb32f(c, nullptr, 0, 0);
+  std::vector<float> lin((size_t)3 * w * h);
+  for (size_t i = 0; i < lin.size(); ++i) { float v = (float)rgb[i] * (1.0f / 255.0f); lin[i] = v * v; }
+  return crt_envmap_set_rgb32f(c, lin.data(), w, h);
+}
+
+int crt_params_set(crt_context* c, const crt_params* p)
+{
+  CRT_REQUIRE(c && p, "null argument");
+  CRT_REQUIRE(p->max_depth >= 1 && p->max_depth <= 64, "max_depth out of range");
+  if (p->frame_seed0 != c->params.frame_seed0) c->rng_valid = false;
+  c->params = *p;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_camera_set(crt_context* c, const crt_camera* cam)
+{
+  CRT_REQUIRE(c && cam, "null argument");
+  c->cam = *cam;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_resize(crt_context* c, uint32_t w, uint32_t h)
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_REQUIRE(w > 0 && h > 0 && (uint64_t)w * h < (1ull << 28), "bad size");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if (w != c->width || h != c->height) {
+    if (c->accum_external) return fail(CRT_ERR_STATE, "unbind the external accumulation buffer before resizing");
+    c->width = w; c->height = h;
+    CRT_CUDA(c->accum_internal.ensure((size_t)w * h));
+    c->accum = c->accum_internal.p;
+    c->state_capacity = 0;
+  }
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_commit(crt_context* c)
+{
+  CRT_REQUIRE(c, "null context");
+  if (c->device < 0) {   // host-only: BVH build + blob, nothing to upload
+    if (c->geometry_dirty) {
+      std::string err;
+      if (!build_blob(c->scene, c->blob, err)) return fail(CRT_ERR_INVALID_ARG, err);
+      c->geometry_dirty = false;
+    }
+    return CRT_OK;
+  }
+  int rc = set_device(c);
+  if (rc) return rc;
+  if (c->geometry_dirty) {
+    std::string err;
+    if (!build_blob(c->scene, c->blob, err)) return fail(CRT_ERR_INVALID_ARG, err);
+    if ((rc = load_blob(c))) return rc;
+    c->geometry_dirty = false;
+    reset_accum_state(c);
+  }
+  return upload_tables(c);
+}
+
+int crt_render_async(crt_context* c, uint32_t n)
+{
+  CRT_REQUIRE(c, "null context");
+  return render_impl(c, n);
+}
+
+int crt_sync(crt_context* c)
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  return CRT_OK;
+}
+
+int crt_render(crt_context* c, uint32_t n, uint64_t* out_total)
+{
+  CRT_REQUIRE(c, "null context");
+  int rc = render_impl(c, n);
+  if (rc) return rc;
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  if (out_total) *out_total = c->next_sample - c->first_sample;
+  return CRT_OK;
+}
+
+int crt_set_next_sample(crt_context* c, uint64_t next_sample)
+{
+  CRT_REQUIRE(c, "null context");
+  c->next_sample = next_sample;
+  return CRT_OK;
+}
+
+int crt_reset_accumulation(crt_context* c, uint64_t first_sample)
+{
+  CRT_REQUIRE(c, "null context");
+  int rc = set_device(c);
+  if (rc) return rc;
+  c->first_sample = first_sample;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+static int display_impl(crt_context* c, const float4* accum, uint8_t* rgb8, size_t stride8, float* rgbf, size_t stridef)
+{
+  if (!c->width || !c->height) return fail(CRT_ERR_STATE, "no render target");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const uint32_t n = c->width * c->height;
+  if (rgb8) CRT_CUDA(c->d_ldr.ensure((size_t)3 * n));
+  if (rgbf) CRT_CUDA(c->d_hdr.ensure((size_t)3 * n));
+  const float ex = exp2f(c->params.exposure);
+  float wp = 1.0f;
+  if (c->params.tone_map) {
+    const float w = c->params.white_point;
+    const float f = fmaf(1.425f, w, 0.05f);
+    wp = (fmaf(w, f, 0.004f)) / (fmaf(w, f + 0.55f, 0.0491f)) - 0.0821f;
+  }
+  {
+    SpanGuard g(c, F_RESOLVE);
+    k_display<<<grid_for(c, 8), 256, 0, c->stream>>>(accum, n, ex, c->params.tone_map, wp,
+                                                     rgb8 ? c->d_ldr.p : nullptr, rgbf ? c->d_hdr.p : nullptr);
+  }
+  CRT_CUDA(cudaGetLastError());
+  if (rgb8) {
+    const size_t row = (size_t)c->width * 3;
+    if (stride8 == 0) stride8 = row;
+    CRT_REQUIRE(stride8 >= row, "stride too small");
+    CRT_CUDA(cudaMemcpy2DAsync(rgb8, stride8, c->d_ldr.p, row, row, c->height, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (rgbf) {
+    const size_t row = (size_t)c->width * 12;
+    if (stridef == 0) stridef = row;
+    CRT_REQUIRE(stridef >= row, "stride too small");
+    CRT_CUDA(cudaMemcpy2DAsync(rgbf, stridef, c->d_hdr.p, row, row, c->height, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  return CRT_OK;
+}
+
+int crt_read_ldr(crt_context* c, uint8_t* rgb8, size_t stride)
+{
+  CRT_REQUIRE(c && rgb8, "null argument");
+  if (!c->accum) return fail(CRT_ERR_STATE, "no accumulation buffer");
+  return display_impl(c, c->accum, rgb8, stride, nullptr, 0);
+}
+
+int crt_read_hdr(crt_context* c, float* rgbf, size_t stride)
+{
+  CRT_REQUIRE(c && rgbf, "null argument");
+  if (!c->accum) return fail(CRT_ERR_STATE, "no accumulation buffer");
+  return display_impl(c, c->accum, nullptr, 0, rgbf, stride);
+}
+
+int crt_read_ldr_from(crt_context* c, const void* device_accum, uint8_t* rgb8, size_t stride)
+{
+  CRT_REQUIRE(c && device_accum && rgb8, "null argument");
+  return display_impl(c, static_cast<const float4*>(device_accum), rgb8, stride, nullptr, 0);
+}
+
+int crt_accum_device_ptr(crt_context* c, void** out_ptr, size_t* out_bytes)
+{
+  CRT_REQUIRE(c && out_ptr, "null argument");
+  *out_ptr = c->accum;
+  if (out_bytes) *out_bytes = sizeof(float4) * (size_t)c->width * c->height;
+  return CRT_OK;
+}
+
+int crt_accum_bind(crt_context* c, void* device_ptr, size_t bytes)
+{
+  CRT_REQUIRE(c, "null context");
+  if (!device_ptr) {
+    c->accum = c->accum_internal.p;
+    c->accum_external = false;
+  } else {
+    CRT_REQUIRE(bytes >= sizeof(float4) * (size_t)c->width * c->height, "bound buffer too small");
+    CRT_REQUIRE(((uintptr_t)device_ptr & 15u) == 0, "bound buffer must be 16-byte aligned");
+    c->accum = static_cast<float4*>(device_ptr);
+    c->accum_external = true;
+  }
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_trace_device(crt_context* c, const void* org4, const void* dir4, uint32_t n, int any_hit, void* hit4, void* inst)
+{
+  CRT_REQUIRE(c && org4 && dir4 && hit4, "null argument");
+  if (!c->has_layout || c->geometry_dirty) return fail(CRT_ERR_STATE, "crt_trace before crt_commit");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if (n == 0) return CRT_OK;
+  const float4* o = static_cast<const float4*>(org4);
+  const float4* d = static_cast<const float4*>(dir4);
+  float4* h = static_cast<float4*>(hit4);
+  int32_t* hi = static_cast<int32_t*>(inst);
+  Counters* gc = c->d_counters.p;
+  const int grid = std::min<int>(grid_for(c, 16), (int)((n + 127u) / 128u));
+  SpanGuard g(c, any_hit ? F_CONNECT : F_EXTEND);
+  if (any_hit) {
+    if (c->stats_on) k_trace<true, true><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
+    else k_trace<true, false><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
+  } else {
+    if (c->stats_on) k_trace<false, true><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
+    else k_trace<false, false><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
+  }
+  CRT_CUDA(cudaGetLastError());
+  return CRT_OK;
+}
+
+int crt_trace(crt_context* c, const float* org, const float* dir, const float* tmax, uint32_t n, int any_hit,
+              int32_t* prim, int32_t* inst, float* t, float* u, float* v)
+{
+  CRT_REQUIRE(c && (n == 0 || (org && dir)), "null argument");
+  if (!c->has_layout || c->geometry_dirty) return fail(CRT_ERR_STATE, "crt_trace before crt_commit");
+  if (n == 0) return CRT_OK;
+  int rc = set_device(c);
+  if (rc) return rc;
+  std::vector<float4> ho(n), hd(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    ho[i] = make_float4(org[3 * (size_t)i], org[3 * (size_t)i + 1], org[3 * (size_t)i + 2], 0.0f);
+    hd[i] = make_float4(dir[3 * (size_t)i], dir[3 * (size_t)i + 1], dir[3 * (size_t)i + 2], tmax ? tmax[i] : CRT_MAXFLOAT);
+  }
+  DevBuf<float4> d_o, d_d, d_h;
+  DevBuf<int32_t> d_i;
+  cudaError_t e = d_o.ensure(n);
+  if (e == cudaSuccess) e = d_d.ensure(n);
+  if (e == cudaSuccess) e = d_h.ensure(n);
+  if (e == cudaSuccess) e = d_i.ensure(n);
+  auto cleanup = [&]() { d_o.release(); d_d.release(); d_h.release(); d_i.release(); };
+  if (e != cudaSuccess) { cleanup(); cudaGetLastError(); return fail(CRT_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+  std::vector<float4> hh(n);
+  std::vector<int32_t> hi(n);
+  e = cudaMemcpyAsync(d_o.p, ho.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d.p, hd.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    rc = crt_trace_device(c, d_o.p, d_d.p, n, any_hit, d_h.p, d_i.p);
+    if (rc) { cleanup(); return rc; }
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hh.data(), d_h.p, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hi.data(), d_i.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(CRT_ERR_CUDA, cudaGetErrorString(e)); }
+  for (uint32_t i = 0; i < n; ++i) {
+    int32_t p;
+    std::memcpy(&p, &hh[i].w, 4);
+    if (prim) prim[i] = p;
+    if (inst) inst[i] = (any_hit && p < 0) ? -1 : hi[i];
+    if (t) t[i] = hh[i].x;
+    if (u) u[i] = hh[i].y;
+    if (v) v[i] = hh[i].z;
+  }
+  return CRT_OK;
+}
+
+int crt_bvh_export(crt_context* c, void* buf, size_t capacity, size_t* out_size)
+{
+  CRT_REQUIRE(c, "null context");
+  if (c->geometry_dirty || c->blob.empty()) return fail(CRT_ERR_STATE, "crt_bvh_export before crt_commit");
+  if (out_size) *out_size = c->blob.size();
+  if (!buf) return CRT_OK;
+  CRT_REQUIRE(capacity >= c->blob.size(), "buffer too small");
+  std::memcpy(buf, c->blob.data(), c->blob.size());
+  return CRT_OK;
+}
+
+int crt_bvh_import(crt_context* c, const void* buf, size_t size)
+{
+  CRT_REQUIRE(c && buf, "null argument");
+  int rc = set_device(c);
+  if (rc) return rc;
+  std::vector<uint8_t> keep(static_cast<const uint8_t*>(buf), static_cast<const uint8_t*>(buf) + size);
+  c->blob.swap(keep);
+  rc = load_blob(c);
+  if (rc) { c->blob.swap(keep); return rc; }
+  c->geometry_dirty = false;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_stats_enable(crt_context* c, int on) { CRT_REQUIRE(c, "null context"); c->stats_on = on != 0; return CRT_OK; }
+
+int crt_stats_reset(crt_context* c)
+{
+  CRT_REQUIRE(c, "null context");
+  int rc = set_device(c);
+  if (rc) return rc;
+  CRT_CUDA(cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), c->stream));
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  collect_spans(c);
+  for (int k = 0; k < F_COUNT; ++k) { c->family_ms[k] = 0.0; c->family_launches[k] = 0; }
+  return CRT_OK;
+}
+
+int crt_stats_get(crt_context* c, crt_stats* out)
+{
+  CRT_REQUIRE(c && out, "null argument");
+  int rc = set_device(c);
+  if (rc) return rc;
+  static_assert(sizeof(Counters) == sizeof(crt_stats), "counter layout");
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  CRT_CUDA(cudaMemcpy(out, c->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+  return CRT_OK;
+}
+
+int crt_timing_enable(crt_context* c, int on) { CRT_REQUIRE(c, "null context"); c->timing_on = on != 0; return CRT_OK; }
+
+int crt_timing_get(crt_context* c, double ms[6], uint64_t launches[6])
+{
+  CRT_REQUIRE(c && ms, "null argument");
+  int rc = set_device(c);
+  if (rc) return rc;
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  collect_spans(c);
+  for (int k = 0; k < F_COUNT; ++k) { ms[k] = c->family_ms[k]; if (launches) launches[k] = c->family_launches[k]; }
+  return CRT_OK;
+}
+
+int crt_stream(crt_context* c, void** out_stream)
+{
+  CRT_REQUIRE(c && out_stream, "null argument");
+  *out_stream = c->stream;
+  return CRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+// host_scene.cpp -- two-level BVH build (binned SAH), blob writer/parser and
+// device layout derivation.  See host_scene.hpp for what this replaces.
+#include "host_scene.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+namespace crt {
+
+namespace {
+
+struct Prim {
+  float lo[3], hi[3], c[3];
+  uint32_t id;
+};
+
+struct TreeNode {
+  float lo[3], hi[3];
+  int32_t a, b;   // inner: child node indices; leaf: first/last primitive (inclusive)
+  bool leaf;
+};
+
+inline float half_area(const float* lo, const float* hi)
+{
+  float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+struct Box {
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
+  float hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  void grow(const float* l, const float* h)
+  {
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); }
+  }
+  void grow_pt(const float* p)
+  {
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
+  }
+};
+
+// Binned SAH builder in the manner of BVH_BinnedBuilder: every node
+// with more than leaf_size primitives and depth < kMaxTreeDepth is split at the
+// cheapest of (nbins-1) planes per axis; primitives are binned by centroid.
+// A degenerate split falls back to an index median.  The two children of a node
+// are allocated next to each other.
+void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<TreeNode>& nodes, int& max_depth)
+{
+  nodes.clear();
+  max_depth = 0;
+  if (prims.empty()) return;
+  struct Work { int node, lo, hi, depth; };
+  std::vector<Work> stack;
+  nodes.push_back(TreeNode{});
+  stack.push_back({ 0, 0, (int)prims.size(), 0 });
+  std::vector<int> bin_count(nbins);
+  std::vector<Box> bin_box(nbins);
+  std::vector<float> right_area(nbins);
+  std::vector<int> right_count(nbins);
+
+  while (!stack.empty()) {
+    Work w = stack.back();
+    stack.pop_back();
+    max_depth = std::max(max_depth, w.depth);
+    Box nb, cb;
+    for (int i = w.lo; i < w.hi; ++i) { nb.grow(prims[i].lo, prims[i].hi); cb.grow_pt(prims[i].c); }
+    TreeNode nd;
+    std::memcpy(nd.lo, nb.lo, 12);
+    std::memcpy(nd.hi, nb.hi, 12);
+    const int count = w.hi - w.lo;
+    if (count <= leaf_size || w.depth >= kMaxTreeDepth) {
+      nd.leaf = true; nd.a = w.lo; nd.b = w.hi - 1;
+      nodes[w.node] = nd;
+      continue;
+    }
+    int best_axis = -1, best_split = -1;
+    float best_cost = FLT_MAX;
+    for (int axis = 0; axis < 3; ++axis) {
+      const float cmin = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+      if (!(ext > 0.0f)) continue;
+      const float scale = (float)nbins / ext;
+      std::fill(bin_count.begin(), bin_count.end(), 0);
+      std::fill(bin_box.begin(), bin_box.end(), Box{});
+      for (int i = w.lo; i < w.hi; ++i) {
+        int b = std::min(nbins - 1, (int)((prims[i].c[axis] - cmin) * scale));
+        bin_count[b]++;
+        bin_box[b].grow(prims[i].lo, prims[i].hi);
+      }
+      Box acc;
+      int cnt = 0;
+      for (int b = nbins - 1; b > 0; --b) {
+        if (bin_count[b]) acc.grow(bin_box[b].lo, bin_box[b].hi);
+        cnt += bin_count[b];
+        right_area[b] = cnt ? half_area(acc.lo, acc.hi) : 0.0f;
+        right_count[b] = cnt;
+      }
+      acc = Box{};
+      cnt = 0;
+      for (int b = 0; b < nbins - 1; ++b) {
+        if (bin_count[b]) acc.grow(bin_box[b].lo, bin_box[b].hi);
+        cnt += bin_count[b];
+        if (cnt == 0 || right_count[b + 1] == 0) continue;
+        float cost = half_area(acc.lo, acc.hi) * (float)cnt + right_area[b + 1] * (float)right_count[b + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
+      }
+    }
+    int mid;
+    if (best_axis >= 0) {
+      const float cmin = cb.lo[best_axis], ext = cb.hi[best_axis] - cb.lo[best_axis];
+      const float scale = (float)nbins / ext;
+      auto it = std::partition(prims.begin() + w.lo, prims.begin() + w.hi, [&](const Prim& p) {
+        int b = std::min(nbins - 1, (int)((p.c[best_axis] - cmin) * scale));
+        return b <= best_split;
+      });
+      mid = (int)(it - prims.begin());
+      if (mid == w.lo || mid == w.hi) mid = w.lo + count / 2;
+    } else {
+      mid = w.lo + count / 2;
+    }
+    nd.leaf = false;
+    nd.a = (int32_t)nodes.size();
+    nd.b = nd.a + 1;
+    nodes[w.node] = nd;
+    nodes.push_back(TreeNode{});
+    nodes.push_back(TreeNode{});
+    stack.push_back({ nd.b, mid, w.hi, w.depth + 1 });
+    stack.push_back({ nd.a, w.lo, mid, w.depth + 1 });
+  }
+}
+
+size_t align16(size_t x) { return (x + 15u) & ~(size_t)15u; }
+
+// Inverse of a row-major 3x4 affine matrix, computed in double.
+bool invert_affine(const float* m, float* out)
+{
+  double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+  double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  if (det == 0.0 || !std::isfinite(det)) return false;
+  double r = 1.0 / det;
+  double inv[9] = { (e * i - f * h) * r, (c * h - b * i) * r, (b * f - c * e) * r,
+                    (f * g - d * i) * r, (a * i - c * g) * r, (c * d - a * f) * r,
+                    (d * h - e * g) * r, (b * g - a * h) * r, (a * e - b * d) * r };
+  double t[3] = { m[3], m[7], m[11] };
+  for (int row = 0; row < 3; ++row) {
+    out[4 * row + 0] = (float)inv[3 * row + 0];
+    out[4 * row + 1] = (float)inv[3 * row + 1];
+    out[4 * row + 2] = (float)inv[3 * row + 2];
+    out[4 * row + 3] = (float)-(inv[3 * row + 0] * t[0] + inv[3 * row + 1] * t[1] + inv[3 * row + 2] * t[2]);
+  }
+  out[12] = 0.0f; out[13] = 0.0f; out[14] = 0.0f; out[15] = 1.0f;
+  return true;
+}
+
+struct MeshTree {
+  std::vector<TreeNode> nodes;
+  std::vector<uint32_t> order;   // BVH order -> caller's triangle index
+  int depth = 0;
+  uint32_t node_off = 0, vert_off = 0, tri_off = 0;
+};
+
+}  // namespace
+
+bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err)
+{
+  const size_t n_mesh = scene.meshes.size();
+  const size_t n_inst = scene.instances.size();
+  std::vector<MeshTree> trees(n_mesh);
+  std::vector<char> used(n_mesh, 0);
+  for (const Instance& in : scene.instances) {
+    if (in.mesh >= n_mesh) { err = "instance refers to an unknown mesh"; return false; }
+    used[in.mesh] = 1;
+  }
+
+  // bottom-level trees, one per referenced mesh
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long mi = 0; mi < (long)n_mesh; ++mi) {
+    if (!used[mi]) continue;
+    const Mesh& m = scene.meshes[mi];
+    const size_t nt = m.idx.size() / 3;
+    std::vector<Prim> prims(nt);
+    for (size_t t = 0; t < nt; ++t) {
+      Prim& p = prims[t];
+      Box b;
+      for (int k = 0; k < 3; ++k) b.grow_pt(&m.pos[3 * (size_t)m.idx[3 * t + k]]);
+      for (int k = 0; k < 3; ++k) { p.lo[k] = b.lo[k]; p.hi[k] = b.hi[k]; p.c[k] = 0.5f * (b.lo[k] + b.hi[k]); }
+      p.id = (uint32_t)t;
+    }
+    build_tree(prims, kBottomLeafSize, kBottomBins, trees[mi].nodes, trees[mi].depth);
+    trees[mi].order.resize(nt);
+    for (size_t t = 0; t < nt; ++t) trees[mi].order[t] = prims[t].id;
+  }
+
+  // offsets
+  uint32_t n_verts = 0, n_tris = 0, n_bottom_nodes = 0;
+  bool any_uv = false;
+  for (size_t mi = 0; mi < n_mesh; ++mi) {
+    if (!used[mi]) continue;
+    trees[mi].vert_off = n_verts;
+    trees[mi].tri_off = n_tris;
+    trees[mi].node_off = n_bottom_nodes;   // rebased below once the top tree size is known
+    n_verts += (uint32_t)(scene.meshes[mi].pos.size() / 3);
+    n_tris += (uint32_t)(scene.meshes[mi].idx.size() / 3);
+    n_bottom_nodes += (uint32_t)trees[mi].nodes.size();
+    any_uv = any_uv || scene.meshes[mi].has_uv;
+  }
+
+  // top-level tree over instance world boxes (8 transformed corners of the mesh root box)
+  std::vector<Prim> iprims(n_inst);
+  std::vector<float> inv(16 * n_inst);
+  for (size_t k = 0; k < n_inst; ++k) {
+    const Instance& in = scene.instances[k];
+    if (!invert_affine(in.xf, &inv[16 * k])) { err = "instance transform is singular"; return false; }
+    const TreeNode& root = trees[in.mesh].nodes[0];
+    Box b;
+    for (int c = 0; c < 8; ++c) {
+      float p[3] = { (c & 1) ? root.hi[0] : root.lo[0], (c & 2) ? root.hi[1] : root.lo[1], (c & 4) ? root.hi[2] : root.lo[2] };
+      float q[3];
+      for (int r = 0; r < 3; ++r)
+        q[r] = in.xf[4 * r] * p[0] + in.xf[4 * r + 1] * p[1] + in.xf[4 * r + 2] * p[2] + in.xf[4 * r + 3];
+      b.grow_pt(q);
+    }
+    Prim& p = iprims[k];
+    for (int r = 0; r < 3; ++r) { p.lo[r] = b.lo[r]; p.hi[r] = b.hi[r]; p.c[r] = 0.5f * (b.lo[r] + b.hi[r]); }
+    p.id = (uint32_t)k;
+  }
+  std::vector<TreeNode> top;
+  int top_depth = 0;
+  build_tree(iprims, kTopLeafSize, kTopBins, top, top_depth);
+  const uint32_t n_top = (uint32_t)top.size();
+  const uint32_t n_nodes = n_inst ? n_top + n_bottom_nodes : 0;
+
+  BlobHeader hdr{};
+  hdr.magic = kBlobMagic; hdr.version = 1;
+  hdr.n_nodes = n_nodes; hdr.n_verts = n_inst ? n_verts : 0; hdr.n_tris = n_inst ? n_tris : 0;
+  hdr.n_inst = (uint32_t)n_inst; hdr.n_top_nodes = n_inst ? n_top : 0;
+  hdr.flags = any_uv ? 1u : 0u;
+  if (n_inst) {
+    for (int k = 0; k < 3; ++k) { hdr.scene_min[k] = top[0].lo[k]; hdr.scene_max[k] = top[0].hi[k]; }
+    float sx = top[0].hi[0] - top[0].lo[0], sy = top[0].hi[1] - top[0].lo[1], sz = top[0].hi[2] - top[0].lo[2];
+    // uSceneEpsilon = max(1e-6, 1e-4 * |box size|), SURVEY A.7
+    hdr.scene_eps = std::max(1.0e-6f, 1.0e-4f * std::sqrt(sx * sx + sy * sy + sz * sz));
+  } else {
+    hdr.scene_eps = 1.0e-6f;
+  }
+
+  size_t off = sizeof(BlobHeader);
+  const size_t o_info = off; off = align16(off + (size_t)16 * hdr.n_nodes);
+  const size_t o_min = off;  off = align16(off + (size_t)12 * hdr.n_nodes);
+  const size_t o_max = off;  off = align16(off + (size_t)12 * hdr.n_nodes);
+  const size_t o_pos = off;  off = align16(off + (size_t)12 * hdr.n_verts);
+  const size_t o_nrm = off;  off = align16(off + (size_t)12 * hdr.n_verts);
+  const size_t o_uv = off;   off = align16(off + (size_t)8 * hdr.n_verts);
+  const size_t o_tri = off;  off = align16(off + (size_t)16 * hdr.n_tris);
+  const size_t o_inv = off;  off = align16(off + (size_t)64 * hdr.n_inst);
+  const size_t o_meta = off; off = align16(off + (size_t)16 * hdr.n_inst);
+  blob.assign(off, 0);
+  std::memcpy(blob.data(), &hdr, sizeof hdr);
+  if (!n_inst) return true;
+
+  int32_t* info = reinterpret_cast<int32_t*>(blob.data() + o_info);
+  float* nmin = reinterpret_cast<float*>(blob.data() + o_min);
+  float* nmax = reinterpret_cast<float*>(blob.data() + o_max);
+  float* pos = reinterpret_cast<float*>(blob.data() + o_pos);
+  float* nrm = reinterpret_cast<float*>(blob.data() + o_nrm);
+  float* uv = reinterpret_cast<float*>(blob.data() + o_uv);
+  int32_t* tri = reinterpret_cast<int32_t*>(blob.data() + o_tri);
+  float* binv = reinterpret_cast<float*>(blob.data() + o_inv);
+  int32_t* meta = reinterpret_cast<int32_t*>(blob.data() + o_meta);
+
+  // top-level nodes: x = 0 inner (y,z children), x = inst+1 leaf (y = bottom root, z = vertex
+  // offset, w = triangle offset) -- SURVEY A.3
+  for (uint32_t n = 0; n < n_top; ++n) {
+    const TreeNode& t = top[n];
+    std::memcpy(nmin + 3 * n, t.lo, 12);
+    std::memcpy(nmax + 3 * n, t.hi, 12);
+    if (t.leaf) {
+      const uint32_t k = iprims[t.a].id;   // leaf size 1
+      const MeshTree& mt = trees[scene.instances[k].mesh];
+      info[4 * n + 0] = (int32_t)k + 1;
+      info[4 * n + 1] = (int32_t)(n_top + mt.node_off);
+      info[4 * n + 2] = (int32_t)mt.vert_off;
+      info[4 * n + 3] = (int32_t)mt.tri_off;
+    } else {
+      info[4 * n + 0] = 0; info[4 * n + 1] = t.a; info[4 * n + 2] = t.b; info[4 * n + 3] = 0;
+    }
+  }
+  for (size_t mi = 0; mi < n_mesh; ++mi) {
+    if (!used[mi]) continue;
+    const MeshTree& mt = trees[mi];
+    const Mesh& m = scene.meshes[mi];
+    const uint32_t base = n_top + mt.node_off;
+    for (size_t n = 0; n < mt.nodes.size(); ++n) {
+      const TreeNode& t = mt.nodes[n];
+      std::memcpy(nmin + 3 * (base + n), t.lo, 12);
+      std::memcpy(nmax + 3 * (base + n), t.hi, 12);
+      int32_t* ni = info + 4 * (base + n);
+      if (t.leaf) { ni[0] = -1; ni[1] = t.a; ni[2] = t.b; ni[3] = 0; }
+      else        { ni[0] = 0;  ni[1] = t.a; ni[2] = t.b; ni[3] = 0; }
+    }
+    const size_t nv = m.pos.size() / 3;
+    std::memcpy(pos + 3 * (size_t)mt.vert_off, m.pos.data(), 12 * nv);
+    std::memcpy(nrm + 3 * (size_t)mt.vert_off, m.nrm.data(), 12 * nv);
+    if (m.has_uv) std::memcpy(uv + 2 * (size_t)mt.vert_off, m.uv.data(), 8 * nv);
+    for (size_t t = 0; t < mt.order.size(); ++t) {
+      const uint32_t src = mt.order[t];
+      int32_t* tr = tri + 4 * ((size_t)mt.tri_off + t);
+      tr[0] = (int32_t)m.idx[3 * src]; tr[1] = (int32_t)m.idx[3 * src + 1]; tr[2] = (int32_t)m.idx[3 * src + 2];
+      tr[3] = (int32_t)src;
+    }
+  }
+  std::memcpy(binv, inv.data(), 64 * n_inst);
+  for (size_t k = 0; k < n_inst; ++k) {
+    const Instance& in = scene.instances[k];
+    meta[4 * k + 0] = (int32_t)in.material;
+    meta[4 * k + 1] = (int32_t)in.mesh;
+    meta[4 * k + 2] = (int32_t)(n_top + trees[in.mesh].node_off);
+    meta[4 * k + 3] = 0;
+  }
+  return true;
+}
+
+bool parse_blob(const void* data, size_t size, BlobView& v, std::string& err)
+{
+  if (!data || size < sizeof(BlobHeader)) { err = "blob too small"; return false; }
+  std::memcpy(&v.hdr, data, sizeof(BlobHeader));
+  if (v.hdr.magic != kBlobMagic || v.hdr.version != 1) { err = "bad blob magic/version"; return false; }
+  const uint8_t* base = static_cast<const uint8_t*>(data);
+  const BlobHeader& h = v.hdr;
+  size_t off = sizeof(BlobHeader);
+  v.node_info = reinterpret_cast<const int32_t*>(base + off); off = align16(off + (size_t)16 * h.n_nodes);
+  v.node_min = reinterpret_cast<const float*>(base + off);    off = align16(off + (size_t)12 * h.n_nodes);
+  v.node_max = reinterpret_cast<const float*>(base + off);    off = align16(off + (size_t)12 * h.n_nodes);
+  v.vert_pos = reinterpret_cast<const float*>(base + off);    off = align16(off + (size_t)12 * h.n_verts);
+  v.vert_nrm = reinterpret_cast<const float*>(base + off);    off = align16(off + (size_t)12 * h.n_verts);
+  v.vert_uv = reinterpret_cast<const float*>(base + off);     off = align16(off + (size_t)8 * h.n_verts);
+  v.tris = reinterpret_cast<const int32_t*>(base + off);      off = align16(off + (size_t)16 * h.n_tris);
+  v.inst_inv = reinterpret_cast<const float*>(base + off);    off = align16(off + (size_t)64 * h.n_inst);
+  v.inst_meta = reinterpret_cast<const int32_t*>(base + off); off = align16(off + (size_t)16 * h.n_inst);
+  if (off > size) { err = "blob truncated"; return false; }
+  if (h.n_top_nodes > h.n_nodes) { err = "blob node counts inconsistent"; return false; }
+  return true;
+}
+
+namespace {
+
+struct Converter {
+  const BlobView& v;
+  DeviceLayout& out;
+  std::string& err;
+  bool ok = true;
+  std::unordered_map<int32_t, int32_t> mesh_root_ref;   // bottom root node -> device ref
+  std::unordered_map<int32_t, int>     mesh_root_depth;
+  int cur_depth_max = 0;
+
+  bool node_ok(int64_t n) const { return n >= 0 && n < (int64_t)v.hdr.n_nodes; }
+
+  void set_box(f4* nd, int child, const float* lo, const float* hi)
+  {
+    f4& nxy = nd[child];
+    nxy.x = lo[0]; nxy.y = hi[0]; nxy.z = lo[1]; nxy.w = hi[1];
+    if (child == 0) { nd[2].x = lo[2]; nd[2].y = hi[2]; }
+    else            { nd[2].z = lo[2]; nd[2].w = hi[2]; }
+  }
+  static float bits(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+  // bottom-level subtree; node indices relative to node_off, triangles relative to tri_off
+  int32_t bottom(int32_t node_abs, int32_t node_off, int32_t tri_off, int depth)
+  {
+    if (!ok) return kRefNone;
+    if (!node_ok(node_abs) || depth > 64) { err = "blob: bottom tree malformed"; ok = false; return kRefNone; }
+    cur_depth_max = std::max(cur_depth_max, depth);
+    const int32_t* info = v.node_info + 4 * (size_t)node_abs;
+    if (info[0] < 0) {
+      const int64_t first = (int64_t)tri_off + info[1], last = (int64_t)tri_off + info[2];
+      if (first < 0 || last < first || last >= (int64_t)v.hdr.n_tris) { err = "blob: leaf range"; ok = false; return kRefNone; }
+      out.tri_verts[3 * (size_t)last + 1].w = bits(1);
+      return (int32_t)(kRefLeafBit | (uint32_t)first);
+    }
+    if (info[0] != 0) { err = "blob: top-level leaf inside a bottom tree"; ok = false; return kRefNone; }
+    const int32_t self = (int32_t)(out.nodes.size() / 4);
+    out.nodes.resize(out.nodes.size() + 4, f4{ 0, 0, 0, 0 });
+    const int32_t l = node_off + info[1], r = node_off + info[2];
+    if (!node_ok(l) || !node_ok(r)) { err = "blob: child index"; ok = false; return kRefNone; }
+    const int32_t rl = bottom(l, node_off, tri_off, depth + 1);
+    const int32_t rr = bottom(r, node_off, tri_off, depth + 1);
+    f4* nd = &out.nodes[4 * (size_t)self];
+    set_box(nd, 0, v.node_min + 3 * (size_t)l, v.node_max + 3 * (size_t)l);
+    set_box(nd, 1, v.node_min + 3 * (size_t)r, v.node_max + 3 * (size_t)r);
+    nd[3].x = bits(rl); nd[3].y = bits(rr);
+    return self;
+  }
+
+  int32_t top(int32_t node_abs, int depth)
+  {
+    if (!ok) return kRefNone;
+    if (!node_ok(node_abs) || depth > 64) { err = "blob: top tree malformed"; ok = false; return kRefNone; }
+    out.max_depth_top = std::max(out.max_depth_top, depth);
+    const int32_t* info = v.node_info + 4 * (size_t)node_abs;
+    if (info[0] > 0) {
+      const int32_t k = info[0] - 1;
+      if (k >= (int32_t)v.hdr.n_inst) { err = "blob: instance index"; ok = false; return kRefNone; }
+      int32_t ref;
+      auto it = mesh_root_ref.find(info[1]);
+      if (it == mesh_root_ref.end()) {
+        cur_depth_max = 0;
+        ref = bottom(info[1], info[1], info[3], 0);
+        mesh_root_ref[info[1]] = ref;
+        out.max_depth_bottom = std::max(out.max_depth_bottom, cur_depth_max);
+      } else {
+        ref = it->second;
+      }
+      f4* ir = &out.inst[4 * (size_t)k];
+      ir[3].x = bits(ref);
+      return (int32_t)(kRefLeafBit | kRefInstBit | (uint32_t)k);
+    }
+    if (info[0] != 0) { err = "blob: bottom leaf inside the top tree"; ok = false; return kRefNone; }
+    const int32_t self = (int32_t)(out.nodes.size() / 4);
+    out.nodes.resize(out.nodes.size() + 4, f4{ 0, 0, 0, 0 });
+    const int32_t l = info[1], r = info[2];
+    if (!node_ok(l) || !node_ok(r)) { err = "blob: child index"; ok = false; return kRefNone; }
+    const int32_t rl = top(l, depth + 1);
+    const int32_t rr = top(r, depth + 1);
+    f4* nd = &out.nodes[4 * (size_t)self];
+    set_box(nd, 0, v.node_min + 3 * (size_t)l, v.node_max + 3 * (size_t)l);
+    set_box(nd, 1, v.node_min + 3 * (size_t)r, v.node_max + 3 * (size_t)r);
+    nd[3].x = bits(rl); nd[3].y = bits(rr);
+    return self;
+  }
+};
+
+}  // namespace
+
+bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
+{
+  out = DeviceLayout{};
+  const BlobHeader& h = v.hdr;
+  out.n_tris = h.n_tris;
+  out.n_inst = h.n_inst;
+  if (h.n_nodes == 0 || h.n_inst == 0) return true;
+
+  // de-indexed triangles: the vertex offset of a triangle is that of the mesh whose
+  // triangle range contains it, taken from the top-level leaf records
+  std::vector<int32_t> tri_voff(h.n_tris, -1);
+  {
+    // mesh triangle ranges: sort distinct (tri_off, vert_off) pairs
+    std::vector<std::pair<int32_t, int32_t>> ranges;
+    for (uint32_t n = 0; n < h.n_top_nodes; ++n) {
+      const int32_t* info = v.node_info + 4 * (size_t)n;
+      if (info[0] > 0) ranges.emplace_back(info[3], info[2]);
+    }
+    std::sort(ranges.begin(), ranges.end());
+    ranges.erase(std::unique(ranges.begin(), ranges.end()), ranges.end());
+    for (size_t r = 0; r < ranges.size(); ++r) {
+      const int64_t lo = ranges[r].first;
+      const int64_t hi = r + 1 < ranges.size() ? ranges[r + 1].first : (int64_t)h.n_tris;
+      if (lo < 0 || hi > (int64_t)h.n_tris) { err = "blob: triangle offsets"; return false; }
+      for (int64_t t = lo; t < hi; ++t) tri_voff[(size_t)t] = ranges[r].second;
+    }
+  }
+  out.tri_verts.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
+  out.tri_nrm.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
+  for (size_t t = 0; t < h.n_tris; ++t) {
+    const int32_t* tr = v.tris + 4 * t;
+    const int32_t vo = tri_voff[t];
+    if (vo < 0) continue;   // triangle of an unreferenced range
+    for (int k = 0; k < 3; ++k) {
+      const int64_t vi = (int64_t)vo + tr[k];
+      if (vi < 0 || vi >= (int64_t)h.n_verts) { err = "blob: vertex index"; return false; }
+      const float* p = v.vert_pos + 3 * (size_t)vi;
+      const float* n = v.vert_nrm + 3 * (size_t)vi;
+      out.tri_verts[3 * t + k] = f4{ p[0], p[1], p[2], 0.0f };
+      out.tri_nrm[3 * t + k] = f4{ n[0], n[1], n[2], 0.0f };
+    }
+    out.tri_verts[3 * t].w = Converter::bits(tr[3]);
+  }
+  out.inst.assign(4 * (size_t)h.n_inst, f4{ 0, 0, 0, 0 });
+  for (size_t k = 0; k < h.n_inst; ++k) {
+    const float* m = v.inst_inv + 16 * k;
+    for (int r = 0; r < 3; ++r) out.inst[4 * k + r] = f4{ m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3] };
+    out.inst[4 * k + 3] = f4{ Converter::bits(kRefNone), Converter::bits(v.inst_meta[4 * k]), 0.0f, 0.0f };
+  }
+  Converter c{ v, out, err };
+  out.top_root = c.top(0, 0);
+  return c.ok;
+}
+
+}  // namespace crt

@@ -1,0 +1,99 @@
+// host_scene.hpp -- host-side scene store, two-level BVH build, blob and device layout.
+//
+// Stands in for OCCT's OpenGl_RaytraceGeometry / OpenGl_TriangleSet /
+// BVH_BinnedBuilder, which CADRays triggers
+// implicitly from V3d_View::Redraw() (src/Launcher/AppViewer.cxx:1047) after
+// AisMesh::Compute hands over a Graphic3d_ArrayOfTriangles
+// (src/ImportExport/AisMesh.cxx:372-423).  CPU code, as in the reference.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace crt {
+
+struct Mesh {
+  std::vector<float>    pos;   // 3 per vertex
+  std::vector<float>    nrm;   // 3 per vertex (geometric normals synthesised when absent)
+  std::vector<float>    uv;    // 2 per vertex (zeros when absent)
+  std::vector<uint32_t> idx;   // 3 per triangle, 0-based
+  bool has_uv = false;
+};
+
+struct Instance {
+  uint32_t mesh;
+  uint32_t material;
+  float    xf[12];             // row-major 3x4 object -> world
+};
+
+struct HostScene {
+  std::vector<Mesh>     meshes;
+  std::vector<Instance> instances;
+};
+
+// "CRTB" blob, version 1 -- layout documented in DESIGN.md.  64-byte header
+// followed by 16-byte aligned sections.
+struct BlobHeader {
+  uint32_t magic, version, n_nodes, n_verts, n_tris, n_inst, n_top_nodes, flags;
+  float    scene_min[3], scene_max[3], scene_eps;
+  uint32_t reserved;
+};
+static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
+constexpr uint32_t kBlobMagic = 0x42545243u;
+
+struct BlobView {
+  BlobHeader     hdr;
+  const int32_t* node_info;
+  const float*   node_min;
+  const float*   node_max;
+  const float*   vert_pos;
+  const float*   vert_nrm;
+  const float*   vert_uv;
+  const int32_t* tris;
+  const float*   inst_inv;
+  const int32_t* inst_meta;
+};
+
+// Builder constants (binned SAH, leaf size 5, depth 32; top level leaf size 1).
+constexpr int kBottomLeafSize = 5;
+constexpr int kTopLeafSize    = 1;
+constexpr int kMaxTreeDepth   = 32;
+constexpr int kBottomBins     = 48;
+constexpr int kTopBins        = 32;
+
+// Builds bottom BVHs per mesh (shared by all its instances), the top BVH over
+// instance world boxes, and serialises everything.  Returns false + message on
+// invalid input.
+bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err);
+bool parse_blob(const void* data, size_t size, BlobView& view, std::string& err);
+
+// Reference encodings of child / root references in the device layout.
+constexpr uint32_t kRefLeafBit = 0x80000000u;
+constexpr uint32_t kRefInstBit = 0x40000000u;
+constexpr int32_t  kRefNone    = 0x7fffffff;       // empty scene
+
+struct f4 { float x, y, z, w; };
+
+// What the kernels walk.  Derived from the blob, never from HostScene, so that
+// crt_bvh_import and crt_commit share one path.
+struct DeviceLayout {
+  // inner nodes only, 64 B each:
+  //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = same for child 1
+  //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (ref0, ref1, 0, 0) as int bits
+  std::vector<f4> nodes;
+  // 3 x float4 per triangle in blob order: v0.w = caller's triangle index bits,
+  // v1.w = 1 if last triangle of its leaf, v2.w = 0
+  std::vector<f4> tri_verts;
+  // 3 x float4 per triangle: vertex normals
+  std::vector<f4> tri_nrm;
+  // 4 x float4 per instance: 3 rows of the inverse matrix, then (rootRef, material, 0, 0) bits
+  std::vector<f4> inst;
+  int32_t top_root = kRefNone;
+  uint32_t n_tris = 0, n_inst = 0;
+  int max_depth_top = 0, max_depth_bottom = 0;
+};
+
+bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err);
+
+}  // namespace crt

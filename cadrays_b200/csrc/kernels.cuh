@@ -1,0 +1,882 @@
+// kernels.cuh -- sm_100a kernels of the wavefront path tracer.
+//
+// Replaces the GLSL programs OCCT runs for CADRays' V3d_View::Redraw()
+// (src/Launcher/AppViewer.cxx:1047): SceneNearestHit / SceneAnyHit (SURVEY 8(a)
+// rows a5-a7), PathTrace + layered BSDF + light sampling (rows a1-a4), RNG (a9),
+// ray generation / accumulation / display (a10).
+//
+// Design: wavefront.  Path state lives in SoA float4 arrays indexed by path slot;
+// compacted queues of slot indices are produced with warp-aggregated atomics
+// (__ballot_sync + __popc, one atomicAdd per warp).  Kernels are launched with a
+// fixed grid sized from the SM count and read the queue length from device memory,
+// so a whole frame is enqueued without a host round trip.
+#pragma once
+#include "device_math.cuh"
+
+namespace crt {
+
+constexpr int kStackSize = 72;            // 32 top + 32 bottom levels + sentinel + slack
+constexpr int32_t kSentinel = 0x7ffffffe; // "leave the instance" marker on the stack
+constexpr int32_t kNoRef = 0x7fffffff;
+
+struct DeviceScene {
+  const float4* __restrict__ nodes;       // 4 x float4 per inner node (see host_scene.hpp)
+  const float4* __restrict__ tri_verts;   // 3 x float4 per triangle
+  const float4* __restrict__ tri_nrm;     // 3 x float4 per triangle
+  const float4* __restrict__ inst;        // 4 x float4 per instance
+  const float4* __restrict__ mats;        // 8 x float4 per material (crt_bsdf)
+  const float4* __restrict__ lights;      // 2 x float4 per light (shader form)
+  const float4* __restrict__ env;         // lat-long texels, rgb_
+  int32_t top_root;
+  uint32_t n_mats, n_lights, env_w, env_h;
+  float scene_eps;
+};
+
+struct DeviceParams {
+  int32_t max_depth;
+  float max_radiance;
+  int32_t two_sided;
+  uint32_t rng_radius;          // 8 in coherent mode else 1
+  float aperture_radius, focal_dist;
+  int32_t env_as_background;    // already and-ed with "a map exists"
+  int32_t russian_roulette;
+  float background[3];
+  // camera basis (host computed, same formulas as the oracle)
+  float eye[3], cu[3], cv[3], cw[3];
+  float hw, hh;
+  int32_t is_ortho;
+  uint32_t width, height;
+  uint32_t tiles_x, tiles_y;    // 8x4 pixel tiles per warp
+};
+
+struct Counters {   // mirrors crt_stats
+  unsigned long long rays_nearest, rays_any, n_inner, n_leaf, n_tri, n_switch, shaded_hits, samples;
+  unsigned long long n_inner_any, n_leaf_any, n_tri_any, n_switch_any;
+};
+
+struct PathState {
+  float4* ray_o;      // o.xyz, w = implicit pdf of the direction (for MIS)
+  float4* ray_d;      // d.xyz, w = bits: bit0 = inside medium
+  float4* thr;        // throughput.xyz, w = bits(rng state)
+  float4* rad;        // radiance.xyz
+  float4* hit;        // t, u, v, bits(triangle slot, -1 = miss)
+  int32_t* hit_inst;
+  uint32_t* queue[2]; // compacted active path slots, ping-pong by depth parity
+  float4* sh_o;       // shadow ray origin.xyz, w = tmax
+  float4* sh_d;       // shadow ray dir.xyz, w = bits(path slot)
+  float4* sh_c;       // throughput * contribution
+  uint32_t* n_active; // [max_depth + 1]
+  uint32_t* n_shadow; // [max_depth]
+};
+
+// ------------------------------------------------------------------ traversal
+
+struct Hit { float t, u, v; int32_t tri; int32_t inst; };
+
+__device__ __forceinline__ float inv_dir(float d)
+{
+  float a = 1.0f / maxf(fabsf(d), 8.271806125530277e-25f);
+  return d < 0.0f ? -a : a;
+}
+
+struct Ray {
+  v3 o, d, inv, oinv;
+  __device__ __forceinline__ void setup(v3 o_, v3 d_)
+  {
+    o = o_; d = d_;
+    inv = V(inv_dir(d.x), inv_dir(d.y), inv_dir(d.z));
+    oinv = V(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+  }
+};
+
+// IntersectTriangle, SURVEY A.4 (same operation order as the oracle's tri_test).
+__device__ __forceinline__ bool tri_test(v3 o, v3 d, v3 p0, v3 p1, v3 p2, float& t, float& u, float& v)
+{
+  v3 e0 = vsub(p1, p0);
+  v3 e1 = vsub(p0, p2);
+  v3 nn = cross3(e1, e0);
+  v3 to = vsub(p0, o);
+  float rcp = 1.0f / dot3(nn, d);
+  float tt = dot3(nn, to) * rcp;
+  v3 k = cross3(d, to);
+  float uu = dot3(k, e1) * rcp;
+  float vv = dot3(k, e0) * rcp;
+  if (tt >= 0.0f && uu >= 0.0f && vv >= 0.0f && uu + vv <= 1.0f) { t = tt; u = uu; v = vv; return true; }
+  return false;
+}
+
+__device__ __forceinline__ v3 xf_point(float4 r0, float4 r1, float4 r2, v3 p)
+{
+  return V(fmaf(r0.z, p.z, fmaf(r0.y, p.y, r0.x * p.x)) + r0.w,
+           fmaf(r1.z, p.z, fmaf(r1.y, p.y, r1.x * p.x)) + r1.w,
+           fmaf(r2.z, p.z, fmaf(r2.y, p.y, r2.x * p.x)) + r2.w);
+}
+__device__ __forceinline__ v3 xf_vector(float4 r0, float4 r1, float4 r2, v3 p)
+{
+  return V(fmaf(r0.z, p.z, fmaf(r0.y, p.y, r0.x * p.x)),
+           fmaf(r1.z, p.z, fmaf(r1.y, p.y, r1.x * p.x)),
+           fmaf(r2.z, p.z, fmaf(r2.y, p.y, r2.x * p.x)));
+}
+
+// SceneNearestHit / SceneAnyHit over the 64-byte two-child nodes.
+// One thread per ray, stack of child references in local memory.  References:
+// >= 0 inner node, bit31 set = leaf (bit30 set = instance, else first triangle).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, float tmax, Hit& hit, Counters& cnt)
+{
+  hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
+  if (S.top_root == kNoRef) return false;
+  if (!(dot3(dir, dir) > 0.0f) || !(dot3(org, org) >= 0.0f)) return false;
+  int32_t stack[kStackSize];
+  int sp = 0;
+  int32_t cur = S.top_root;
+  int32_t inst = -1;
+  Ray r;
+  r.setup(org, dir);
+  bool found = false;
+  for (;;) {
+    if (cur >= 0) {
+      // ---- inner node: test both children, descend into the nearer one
+      if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
+      const float4* nd = S.nodes + 4 * (size_t)cur;
+      const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+      const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
+      const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
+      const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
+      const float c1x0 = fmaf(n1.x, r.inv.x, r.oinv.x), c1x1 = fmaf(n1.y, r.inv.x, r.oinv.x);
+      const float c1y0 = fmaf(n1.z, r.inv.y, r.oinv.y), c1y1 = fmaf(n1.w, r.inv.y, r.oinv.y);
+      const float c1z0 = fmaf(n2.z, r.inv.z, r.oinv.z), c1z1 = fmaf(n2.w, r.inv.z, r.oinv.z);
+      const float te0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fminf(c0z0, c0z1));
+      const float tx0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fmaxf(c0z0, c0z1));
+      const float te1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fminf(c1z0, c1z1));
+      const float tx1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fmaxf(c1z0, c1z1));
+      const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
+      const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
+      const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        const bool swap = te1 < te0;
+        cur = swap ? r1 : r0;
+        stack[sp++] = swap ? r0 : r1;
+        continue;
+      }
+      if (h0) { cur = r0; continue; }
+      if (h1) { cur = r1; continue; }
+    } else if ((uint32_t)cur & 0x40000000u) {
+      // ---- top-level leaf: enter the instance (ray to object space, not renormalised)
+      if (COUNT) { if (ANY) cnt.n_switch_any++; else cnt.n_switch++; }
+      inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
+      const float4* ir = S.inst + 4 * (size_t)inst;
+      const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+      r.setup(xf_point(m0, m1, m2, org), xf_vector(m0, m1, m2, dir));
+      stack[sp++] = kSentinel;
+      cur = __float_as_int(m3.x);
+      continue;
+    } else {
+      // ---- bottom-level leaf: triangles until the "last" flag
+      if (COUNT) { if (ANY) cnt.n_leaf_any++; else cnt.n_leaf++; }
+      uint32_t tri = (uint32_t)cur & 0x3fffffffu;
+      for (;;) {
+        if (COUNT) { if (ANY) cnt.n_tri_any++; else cnt.n_tri++; }
+        const float4* tv = S.tri_verts + 3 * (size_t)tri;
+        const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+        float t, u, v;
+        if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
+          hit.t = t; hit.u = u; hit.v = v; hit.tri = (int32_t)tri; hit.inst = inst;
+          found = true;
+          if (ANY) return true;
+        }
+        if (__float_as_int(b.w) != 0) break;
+        ++tri;
+      }
+    }
+    // ---- pop
+    if (sp == 0) break;
+    cur = stack[--sp];
+    if (cur == kSentinel) {
+      r.setup(org, dir);
+      if (sp == 0) break;
+      cur = stack[--sp];
+    }
+  }
+  return found;
+}
+
+// ------------------------------------------------------------------ BSDF
+
+struct Bsdf {
+  v3 Kc; float Kc_w;
+  v3 Kd;
+  v3 Ks; float Ks_w;
+  v3 Kt;
+  v3 Fc, Fb;
+};
+
+__device__ __forceinline__ float fresnel_dielectric4(float cos_i, float cos_t, float eta_i, float eta_t)
+{
+  float parl = (eta_t * cos_i - eta_i * cos_t) / (eta_t * cos_i + eta_i * cos_t);
+  float perp = (eta_i * cos_i - eta_t * cos_t) / (eta_i * cos_i + eta_t * cos_t);
+  return (parl * parl + perp * perp) * 0.5f;
+}
+
+__device__ __forceinline__ float fresnel_dielectric(float cos_i, float index)
+{
+  float eta_i = cos_i > 0.0f ? 1.0f : index;
+  float eta_t = cos_i > 0.0f ? index : 1.0f;
+  float sin_t2 = (eta_i * eta_i) / (eta_t * eta_t) * (1.0f - cos_i * cos_i);
+  if (sin_t2 < 1.0f) return fresnel_dielectric4(fabsf(cos_i), sqrtf(1.0f - sin_t2), eta_i, eta_t);
+  return 1.0f;
+}
+
+__device__ __forceinline__ float fresnel_conductor(float cos_i, float eta, float k)
+{
+  float tmp = 2.0f * eta * cos_i;
+  float tmp1 = eta * eta + k * k;
+  float s_perp = (tmp1 - tmp + cos_i * cos_i) / (tmp1 + tmp + cos_i * cos_i);
+  float tmp2 = tmp1 * cos_i * cos_i;
+  float s_parl = (tmp2 - tmp + 1.0f) / (tmp2 + tmp + 1.0f);
+  return (s_perp + s_parl) * 0.5f;
+}
+
+// Graphic3d_Fresnel::Serialize() encoding (MaterialEditor.cxx:209-255).
+__device__ __forceinline__ v3 fresnel_media(float cos_i, v3 f)
+{
+  if (f.x > -0.5f) {
+    float m = 1.0f - fabsf(cos_i);
+    float m2 = m * m;
+    float m5 = m2 * m2 * m;
+    return V(f.x + (1.0f - f.x) * m5, f.y + (1.0f - f.y) * m5, f.z + (1.0f - f.z) * m5);
+  }
+  if (f.x > -1.5f) return V(f.z, f.z, f.z);
+  if (f.x > -2.5f) { float c = fresnel_conductor(fabsf(cos_i), f.y, f.z); return V(c, c, c); }
+  float c = fresnel_dielectric(cos_i, f.y);
+  return V(c, c, c);
+}
+
+__device__ __forceinline__ float ggx_d(float mz, float a)
+{
+  float a2 = a * a;
+  float q = fmaf(mz * mz, a2 - 1.0f, 1.0f);
+  return a2 / (CRT_PI * q * q);
+}
+
+__device__ __forceinline__ float smith_g1(v3 dir, v3 m, float a)
+{
+  if (dot3(dir, m) * dir.z <= 0.0f) return 0.0f;
+  float c2 = dir.z * dir.z;
+  float tan2 = (1.0f - c2) / c2;
+  return 2.0f / (1.0f + sqrtf(fmaf(a * a, tan2, 1.0f)));
+}
+
+__device__ __forceinline__ v3 eval_ggx(v3 wi, v3 wo, v3 fresnel, float a)
+{
+  if (wi.z <= 0.0f || wo.z <= 0.0f) return V(0, 0, 0);
+  v3 h = normalize3(vadd(wi, wo));
+  float d = ggx_d(h.z, a);
+  float g = smith_g1(wo, h, a) * smith_g1(wi, h, a);
+  return vscale(fresnel_media(dot3(wo, h), fresnel), d * g / (4.0f * wo.z));
+}
+
+__device__ __forceinline__ float eval_lambert(v3 wi, v3 wo)
+{
+  return (wi.z <= 0.0f || wo.z <= 0.0f) ? 0.0f : wi.z * CRT_INV_PI;
+}
+
+__device__ __forceinline__ v3 eval_bsdf_layered(const Bsdf& b, v3 wi, v3 wo, bool two_sided)
+{
+  if (two_sided) { wi.z = fabsf(wi.z); wo.z = fabsf(wo.z); }
+  v3 r = vscale(b.Kd, eval_lambert(wi, wo));
+  if (b.Ks_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Ks, eval_ggx(wi, wo, b.Fb, b.Ks_w)));
+  v3 cf = fresnel_media(wo.z, b.Fc);
+  r = vmul(r, V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z));
+  if (b.Kc_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Kc, eval_ggx(wi, wo, b.Fc, b.Kc_w)));
+  return r;
+}
+
+__device__ __forceinline__ float ggx_pdf_term(float hz, float a, float wi_dot_h)
+{
+  return ggx_d(hz, a) * fabsf(hz) * 0.25f / wi_dot_h;
+}
+
+__device__ __forceinline__ float bsdf_pdf_layered(const Bsdf& b, v3 wo, v3 wi, v3 weight)
+{
+  v3 cf = fresnel_media(wo.z, b.Fc);
+  v3 ct = V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z);
+  float pc = dot3(vmul(b.Kc, cf), weight);
+  float pd = dot3(vmul(b.Kd, ct), weight);
+  float ps = dot3(vmul(b.Ks, ct), weight);
+  float pt = dot3(vmul(b.Kt, ct), weight);
+  float pdf = 0.0f;
+  if (wi.z * wo.z > 0.0f) {
+    v3 h = normalize3(vadd(wi, wo));
+    float wh = dot3(wi, h);
+    pdf = pd * fabsf(wi.z * CRT_INV_PI);
+    if (b.Kc_w > CRT_FLT_EPS) pdf += pc * ggx_pdf_term(h.z, b.Kc_w, wh);
+    if (b.Ks_w > CRT_FLT_EPS) pdf += ps * ggx_pdf_term(h.z, b.Ks_w, wh);
+  }
+  return pdf / ((pc + pd) + (ps + pt));
+}
+
+__device__ __forceinline__ v3 sample_lambert(v3 wo, v3& wi, float& pdf, uint32_t& rng, bool two_sided)
+{
+  float k1 = rand_float(rng);
+  float k2 = rand_float(rng);
+  float sn, cs;
+  sincos2pi(k1, sn, cs);
+  float r = sqrtf(k2);
+  v3 w = V(cs * r, sn * r, sqrtf(1.0f - k2));
+  if (two_sided && wo.z < 0.0f) w.z = -w.z;
+  wi = w;
+  pdf *= fabsf(w.z) * CRT_INV_PI;
+  if (two_sided) return V(1, 1, 1);
+  return wo.z >= 0.0f ? V(1, 1, 1) : V(0, 0, 0);
+}
+
+__device__ __forceinline__ v3 sample_ggx(v3 wo, v3& wi, v3 fresnel, float a, float& pdf, uint32_t& rng, bool two_sided)
+{
+  float k1 = rand_float(rng);
+  float k2 = rand_float(rng);
+  float tan2 = a * a * k1 / (1.0f - k1);
+  float cos_m = 1.0f / sqrtf(1.0f + tan2);
+  float sin_m = sqrtf(maxf(1.0f - cos_m * cos_m, 0.0f));
+  float sn, cs;
+  sincos2pi(k2, sn, cs);
+  v3 m = V(cs * sin_m, sn * sin_m, cos_m);
+  pdf *= ggx_d(cos_m, a) * cos_m;
+  bool flip = two_sided && wo.z < 0.0f;
+  if (flip) wo.z = -wo.z;
+  float cos_d = dot3(wo, m);
+  v3 w = V(fmaf(2.0f * cos_d, m.x, -wo.x), fmaf(2.0f * cos_d, m.y, -wo.y), fmaf(2.0f * cos_d, m.z, -wo.z));
+  wi = w;
+  if (w.z <= 0.0f || wo.z <= 0.0f) return V(0, 0, 0);
+  pdf /= 4.0f * cos_d;
+  float g = smith_g1(wo, m, a) * smith_g1(w, m, a);
+  if (flip) wi.z = -w.z;
+  return vscale(fresnel_media(cos_d, fresnel), (g * cos_d) / (wo.z * cos_m));
+}
+
+__device__ __forceinline__ v3 transmitted(float index, v3 wo)
+{
+  float eta = wo.z > 0.0f ? 1.0f / index : index;
+  float sin_t2 = eta * eta * (1.0f - wo.z * wo.z);
+  float cos_t = sqrtf(1.0f - minf(sin_t2, 1.0f));
+  if (wo.z > 0.0f) cos_t = -cos_t;
+  return normalize3(V(-eta * wo.x, -eta * wo.y, cos_t));
+}
+
+__device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& wi, v3& weight, bool& inside,
+                                                     uint32_t& rng, bool two_sided)
+{
+  float pdf = 0.0f;
+  v3 cf = fresnel_media(wo.z, b.Fc);
+  v3 ct = V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z);
+  float pc = dot3(vmul(b.Kc, cf), weight);
+  float pd = dot3(vmul(b.Kd, ct), weight);
+  float ps = dot3(vmul(b.Ks, ct), weight);
+  float pt = dot3(vmul(b.Kt, ct), weight);
+  float total = (pc + pd) + (ps + pt);
+  float ksi = total * rand_float(rng);
+  wi = V(0, 0, 1);
+  if (ksi < pc) {
+    pdf = pc / total;
+    weight = vmul(weight, vscale(b.Kc, 1.0f / pdf));
+    if (b.Kc_w < CRT_FLT_EPS) {
+      weight = vmul(weight, cf);
+      wi = V(-wo.x, -wo.y, wo.z);
+      pdf = CRT_MAXFLOAT;
+    } else {
+      weight = vmul(weight, sample_ggx(wo, wi, b.Fc, b.Kc_w, pdf, rng, two_sided));
+    }
+  } else if (ksi < total) {
+    weight = vmul(weight, ct);
+    if (ksi < pc + pd) {
+      pdf = pd / total;
+      weight = vmul(weight, vscale(b.Kd, 1.0f / pdf));
+      weight = vmul(weight, sample_lambert(wo, wi, pdf, rng, two_sided));
+    } else if (ksi < (pc + pd) + ps) {
+      pdf = ps / total;
+      weight = vmul(weight, vscale(b.Ks, 1.0f / pdf));
+      if (b.Ks_w < CRT_FLT_EPS) {
+        weight = vmul(weight, fresnel_media(wo.z, b.Fb));
+        wi = V(-wo.x, -wo.y, wo.z);
+        pdf = CRT_MAXFLOAT;
+      } else {
+        weight = vmul(weight, sample_ggx(wo, wi, b.Fb, b.Ks_w, pdf, rng, two_sided));
+      }
+    } else {
+      pdf = pt / total;
+      weight = vmul(weight, vscale(b.Kt, 1.0f / pdf));
+      float index = b.Fc.x > -2.5f ? 1.0f : b.Fc.y;
+      wi = transmitted(index, wo);
+      inside = !inside;
+      pdf = CRT_MAXFLOAT;
+    }
+  }
+  if (!(total >= CRT_FLT_EPS)) weight = V(0, 0, 0);
+  return pdf;
+}
+
+// ------------------------------------------------------------------ frame, lights, env
+
+struct Frame { v3 x, y, z; };
+
+__device__ __forceinline__ Frame build_frame(v3 n)
+{
+  v3 ax = V(n.z, 0.0f, -n.x);
+  v3 ay = V(0.0f, -n.z, n.y);
+  float lx = dot3(ax, ax), ly = dot3(ay, ay);
+  Frame f;
+  if (lx > ly) {
+    ax = vscale(ax, 1.0f / sqrtf(lx));
+    ay = cross3(ax, n);
+  } else {
+    ay = vscale(ay, 1.0f / sqrtf(ly));
+    ax = cross3(ay, n);
+  }
+  f.x = ax; f.y = ay; f.z = n;
+  return f;
+}
+__device__ __forceinline__ v3 to_local(v3 v, const Frame& f) { return V(dot3(v, f.x), dot3(v, f.y), dot3(v, f.z)); }
+__device__ __forceinline__ v3 from_local(v3 v, const Frame& f)
+{
+  return vadd(vadd(vscale(f.x, v.x), vscale(f.y, v.y)), vscale(f.z, v.z));
+}
+
+__device__ __forceinline__ float cone_pdf(float cos_max) { return 1.0f / (CRT_2PI - cos_max * CRT_2PI); }
+
+__device__ __forceinline__ v3 ld_rgb(const float4* p, int i) { float4 t = __ldg(p + i); return V(t.x, t.y, t.z); }
+
+__device__ __forceinline__ v3 env_lookup(const DeviceScene& S, v3 d)
+{
+  if (S.env_w == 0) return V(0, 0, 0);
+  float u = (atan2_poly(d.y, d.x) + CRT_PI) * CRT_INV_2PI;
+  float v = acos_poly(d.z) * CRT_INV_PI;
+  float fx = fmaf(u, (float)S.env_w, -0.5f);
+  float fy = fmaf(v, (float)S.env_h, -0.5f);
+  float flx = floorf(fx), fly = floorf(fy);
+  float ax = fx - flx, ay = fy - fly;
+  int x0 = (int)flx, y0 = (int)fly;
+  int w = (int)S.env_w, h = (int)S.env_h;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = ((x0 % w) + w) % w; x1 = ((x1 % w) + w) % w;
+  y0 = y0 < 0 ? 0 : (y0 > h - 1 ? h - 1 : y0);
+  y1 = y1 < 0 ? 0 : (y1 > h - 1 ? h - 1 : y1);
+  v3 c00 = ld_rgb(S.env, y0 * w + x0), c10 = ld_rgb(S.env, y0 * w + x1);
+  v3 c01 = ld_rgb(S.env, y1 * w + x0), c11 = ld_rgb(S.env, y1 * w + x1);
+  v3 top = vadd(vscale(c00, 1.0f - ax), vscale(c10, ax));
+  v3 bot = vadd(vscale(c01, 1.0f - ax), vscale(c11, ax));
+  return vadd(vscale(top, 1.0f - ay), vscale(bot, ay));
+}
+
+// IntersectLight, SURVEY A.7.
+__device__ __forceinline__ v3 intersect_light(const DeviceScene& S, const DeviceParams& P, v3 o, v3 d, int depth,
+                                              float hit_dist, float& pdf_out)
+{
+  v3 total = V(0, 0, 0);
+  float pdf = 0.0f;
+  const float inv_n = S.n_lights ? 1.0f / (float)S.n_lights : 0.0f;
+  const bool miss = hit_dist == CRT_MAXFLOAT;
+  for (uint32_t i = 0; i < S.n_lights; ++i) {
+    const float4 e = __ldg(S.lights + 2 * i), p = __ldg(S.lights + 2 * i + 1);
+    if (p.w != 0.0f) {
+      v3 to = vsub(V(p.x, p.y, p.z), o);
+      float dist = sqrtf(dot3(to, to));
+      if (dist < hit_dist) {
+        float cos_max = 1.0f / sqrtf(1.0f + (e.w * e.w) / (dist * dist));
+        if (cos_max < 1.0f && dot3(d, vscale(to, 1.0f / dist)) >= cos_max) {
+          hit_dist = dist;
+          total = V(e.x, e.y, e.z);
+          pdf = inv_n * cone_pdf(cos_max);
+        }
+      }
+    } else if (hit_dist == CRT_MAXFLOAT) {
+      if (e.w < 1.0f && dot3(d, V(p.x, p.y, p.z)) >= e.w) {
+        total = vadd(total, V(e.x, e.y, e.z));
+        pdf += inv_n * cone_pdf(e.w);
+      }
+    }
+  }
+  if (pdf == 0.0f && miss && hit_dist == CRT_MAXFLOAT) {
+    if (depth == 0 && !P.env_as_background) total = V(P.background[0], P.background[1], P.background[2]);
+    else total = env_lookup(S, d);
+  }
+  pdf_out = pdf;
+  return total;
+}
+
+// SampleLight, SURVEY A.7.
+__device__ __forceinline__ v3 sample_light(v3 to_light, float dist, bool infinite, float smooth, float& pdf, uint32_t& rng)
+{
+  Frame f = build_frame(vscale(to_light, 1.0f / dist));
+  float cos_max = infinite ? smooth : 1.0f / sqrtf(1.0f + (smooth * smooth) / (dist * dist));
+  float k1 = rand_float(rng);
+  float k2 = rand_float(rng);
+  float tz = 1.0f - k2 * (1.0f - cos_max);
+  float sn, cs;
+  sincos2pi(k1, sn, cs);
+  float r = sqrtf(maxf(1.0f - tz * tz, 0.0f));
+  pdf = (cos_max < 1.0f) ? pdf * cone_pdf(cos_max) : CRT_MAXFLOAT;
+  return normalize3(from_local(V(cs * r, sn * r, tz), f));
+}
+
+// ------------------------------------------------------------------ queue helpers
+
+// Appends one entry per lane with pred set; one atomicAdd per warp.  Must be
+// called by all 32 lanes.
+__device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool pred)
+{
+  const unsigned mask = __ballot_sync(0xffffffffu, pred);
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == 0 && mask) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void flush_counters(Counters* g, const Counters& c)
+{
+  // warp-reduce then one atomic per warp and field
+  unsigned long long v[12] = { c.rays_nearest, c.rays_any, c.n_inner, c.n_leaf, c.n_tri, c.n_switch, c.shaded_hits, c.samples,
+                               c.n_inner_any, c.n_leaf_any, c.n_tri_any, c.n_switch_any };
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(g);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);
+  }
+}
+
+// ------------------------------------------------------------------ kernels
+
+// GenerateRay for every path slot of the batch.  Slot layout: sample k
+// of the batch occupies slots [k*tiles*32, (k+1)*tiles*32); inside, each warp owns
+// an 8x4 pixel tile so primary rays of a warp are coherent.
+__global__ void __launch_bounds__(256)
+k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seeds, uint32_t n_batch)
+{
+  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t total = per_sample * n_batch;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += stride) {
+    const uint32_t slot = base + (threadIdx.x & 31u);
+    const uint32_t k = slot / per_sample;
+    const uint32_t in = slot - k * per_sample;
+    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
+    const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
+    const bool valid = slot < total && px < P.width && py < P.height;
+    if (valid) {
+      uint32_t rng = seed_rand(__ldg(frame_seeds + k), px, py, P.width, P.rng_radius);
+      const float jx = rand_float(rng);
+      const float jy = rand_float(rng);
+      float la = 0.0f, lb = 0.0f;
+      if (P.aperture_radius > 0.0f) { la = rand_float(rng); lb = rand_float(rng); }
+      const float fx = ((float)px + jx) / (float)P.width;
+      const float fy = ((float)py + jy) / (float)P.height;
+      const float sx = fmaf(fx, 2.0f, -1.0f) * P.hw;
+      const float sy = fmaf(fy, 2.0f, -1.0f) * P.hh;
+      const v3 eye = V(P.eye[0], P.eye[1], P.eye[2]);
+      const v3 cu = V(P.cu[0], P.cu[1], P.cu[2]), cv = V(P.cv[0], P.cv[1], P.cv[2]), cw = V(P.cw[0], P.cw[1], P.cw[2]);
+      v3 o, d;
+      if (P.is_ortho) {
+        o = vadd(eye, vadd(vscale(cu, sx), vscale(cv, sy)));
+        d = cw;
+      } else {
+        o = eye;
+        d = normalize3(vadd(cw, vadd(vscale(cu, sx), vscale(cv, sy))));
+      }
+      if (P.aperture_radius > 0.0f) {
+        const float ft = P.focal_dist / dot3(d, cw);
+        const v3 focus = vadd(o, vscale(d, ft));
+        float sn, cs;
+        sincos2pi(lb, sn, cs);
+        const float r = sqrtf(la) * P.aperture_radius;
+        o = vadd(o, vadd(vscale(cu, r * cs), vscale(cv, r * sn)));
+        d = normalize3(vsub(focus, o));
+      }
+      st.ray_o[slot] = make_float4(o.x, o.y, o.z, 1.0f);
+      st.ray_d[slot] = make_float4(d.x, d.y, d.z, __int_as_float(0));
+      st.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng));
+      st.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    const uint32_t at = warp_push(st.n_active, valid);
+    if (valid) st.queue[0][at] = slot;
+  }
+}
+
+// SceneNearestHit for every active path.
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
+{
+  const uint32_t n = st.n_active[depth];
+  const uint32_t* __restrict__ q = st.queue[depth & 1];
+  Counters cnt = {};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = q[i];
+    const float4 o = st.ray_o[slot], d = st.ray_d[slot];
+    Hit hit;
+    traverse<false, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), CRT_MAXFLOAT, hit, cnt);
+    if (COUNT) cnt.rays_nearest++;
+    st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+    st.hit_inst[slot] = hit.inst;
+  }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// One bounce of PathTrace for every active path: implicit
+// light / environment hit with MIS, emission, next-event estimation (emits a
+// shadow ray), Beer-Lambert absorption, layered-BSDF sampling, termination /
+// Russian roulette, continuation ray.
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
+{
+  const uint32_t n = st.n_active[depth];
+  const uint32_t* __restrict__ q = st.queue[depth & 1];
+  uint32_t* __restrict__ qn = st.queue[(depth + 1) & 1];
+  Counters cnt = {};
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const bool two_sided = P.two_sided != 0;
+  const float eps = S.scene_eps;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+    const uint32_t i = base + (threadIdx.x & 31u);
+    const bool valid = i < n;
+    bool want_shadow = false, want_next = false;
+    uint32_t slot = 0;
+    v3 sh_o = V(0, 0, 0), sh_d = V(0, 0, 0), sh_c = V(0, 0, 0);
+    float sh_tmax = 0.0f;
+    v3 org = V(0, 0, 0), dir = V(0, 0, 1), thr = V(0, 0, 0);
+    float imp_pdf = 1.0f;
+    uint32_t rng = 0;
+    bool inside = false;
+    if (valid) {
+      slot = q[i];
+      const float4 ro = st.ray_o[slot], rd = st.ray_d[slot], tw = st.thr[slot], hh = st.hit[slot];
+      float4 rr = st.rad[slot];
+      org = V(ro.x, ro.y, ro.z); dir = V(rd.x, rd.y, rd.z);
+      imp_pdf = ro.w;
+      inside = (__float_as_int(rd.w) & 1) != 0;
+      thr = V(tw.x, tw.y, tw.z);
+      rng = __float_as_uint(tw.w);
+      const int32_t tri = __float_as_int(hh.w);
+      const bool found = tri >= 0;
+      v3 radiance = V(rr.x, rr.y, rr.z);
+
+      float exp_pdf;
+      const v3 le = intersect_light(S, P, org, dir, depth, hh.x, exp_pdf);
+      if (any_gt(le, 0.0f) || !found) {
+        const float mis = (depth == 0 || imp_pdf == CRT_MAXFLOAT) ? 1.0f
+                        : imp_pdf * imp_pdf / (exp_pdf * exp_pdf + imp_pdf * imp_pdf);
+        radiance = vadd(radiance, vscale(vmul(thr, le), mis));
+      } else {
+        const int32_t inst = st.hit_inst[slot];
+        const float4* ir = S.inst + 4 * (size_t)inst;
+        const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+        const v3 c0 = V(m0.x, m1.x, m2.x), c1 = V(m0.y, m1.y, m2.y), c2 = V(m0.z, m1.z, m2.z);
+        // geometric normal from the stored vertices (same expression as tri_test's nn)
+        const float4* tv = S.tri_verts + 3 * (size_t)tri;
+        const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+        const v3 p0 = V(a.x, a.y, a.z), p1 = V(b.x, b.y, b.z), p2 = V(c.x, c.y, c.z);
+        const v3 nraw = cross3(vsub(p0, p2), vsub(p1, p0));
+        const v3 ng = normalize3(V(dot3(c0, nraw), dot3(c1, nraw), dot3(c2, nraw)));
+        org = vadd(org, vscale(dir, hh.x));
+        // SmoothNormal, SURVEY A.4
+        const float4* tn = S.tri_nrm + 3 * (size_t)tri;
+        const v3 n0 = ld_rgb(tn, 0), n1 = ld_rgb(tn, 1), n2 = ld_rgb(tn, 2);
+        v3 ns = vadd(vadd(vscale(n1, hh.y), vscale(n2, hh.z)), vscale(n0, (1.0f - hh.y) - hh.z));
+        ns = normalize3(ns);
+        ns = normalize3(V(dot3(c0, ns), dot3(c1, ns), dot3(c2, ns)));
+        const Frame frame = build_frame(ns);
+
+        const uint32_t mat_id = (uint32_t)__float_as_int(m3.y);
+        Bsdf B;
+        v3 mat_le, absorp;
+        float absorp_k;
+        if (mat_id < S.n_mats) {
+          const float4* mp = S.mats + 8 * (size_t)mat_id;
+          const float4 kc = __ldg(mp), kd = __ldg(mp + 1), ks = __ldg(mp + 2), kt = __ldg(mp + 3);
+          const float4 le4 = __ldg(mp + 4), fc = __ldg(mp + 5), fb = __ldg(mp + 6), ab = __ldg(mp + 7);
+          B.Kc = V(kc.x, kc.y, kc.z); B.Kc_w = kc.w;
+          B.Kd = V(kd.x, kd.y, kd.z);
+          B.Ks = V(ks.x, ks.y, ks.z); B.Ks_w = ks.w;
+          B.Kt = V(kt.x, kt.y, kt.z);
+          B.Fc = V(fc.x, fc.y, fc.z); B.Fb = V(fb.x, fb.y, fb.z);
+          mat_le = V(le4.x, le4.y, le4.z);
+          absorp = V(ab.x, ab.y, ab.z); absorp_k = ab.w;
+        } else {   // default grey diffuse (same record as the oracle's k_default_bsdf)
+          B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kd = V(0.8f, 0.8f, 0.8f); B.Ks = V(0, 0, 0); B.Ks_w = 0.0f;
+          B.Kt = V(0, 0, 0); B.Fc = V(-1.0f, 0.0f, 0.0f); B.Fb = V(-1.0f, 0.0f, 1.0f);
+          mat_le = V(0, 0, 0); absorp = V(0, 0, 0); absorp_k = 0.0f;
+        }
+        if (COUNT) cnt.shaded_hits++;
+
+        const v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), frame);
+        radiance = vadd(radiance, vmul(thr, mat_le));
+
+        const v3 nee_k = vadd(B.Kd, vadd(B.Ks_w > CRT_FLT_EPS ? B.Ks : V(0, 0, 0), B.Kc_w > CRT_FLT_EPS ? B.Kc : V(0, 0, 0)));
+        if (S.n_lights > 0 && dot3(nee_k, thr) > 0.0f) {
+          exp_pdf = 1.0f / (float)S.n_lights;
+          int li = (int)(rand_float(rng) * (float)S.n_lights);
+          if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+          const float4 le_w = __ldg(S.lights + 2 * li), lp = __ldg(S.lights + 2 * li + 1);
+          const bool infinite = lp.w == 0.0f;
+          const v3 to = infinite ? V(lp.x, lp.y, lp.z) : vsub(V(lp.x, lp.y, lp.z), org);
+          const float dist = sqrtf(dot3(to, to));
+          const v3 ldir = sample_light(to, dist, infinite, le_w.w, exp_pdf, rng);
+          const v3 wl = to_local(ldir, frame);
+          const float bpdf = bsdf_pdf_layered(B, wo, wl, thr);
+          imp_pdf = bpdf;
+          const float mis = (exp_pdf == CRT_MAXFLOAT) ? 1.0f : exp_pdf / (exp_pdf * exp_pdf + bpdf * bpdf);
+          const v3 contrib = vscale(vmul(V(le_w.x, le_w.y, le_w.z), eval_bsdf_layered(B, wl, wo, two_sided)), mis);
+          if (any_gt(contrib, CRT_MIN_CONTRIBUTION)) {
+            const float side = dot3(ng, ldir) >= 0.0f ? eps : -eps;
+            sh_o = vadd(vadd(org, vscale(ldir, eps)), vscale(ng, side));
+            sh_d = ldir;
+            sh_tmax = infinite ? CRT_MAXFLOAT : dist;
+            sh_c = vmul(thr, contrib);
+            want_shadow = true;
+          }
+        }
+
+        if (inside) {
+          thr = vmul(thr, V(exp_poly(-hh.x * absorp_k * (1.0f - absorp.x)),
+                            exp_poly(-hh.x * absorp_k * (1.0f - absorp.y)),
+                            exp_poly(-hh.x * absorp_k * (1.0f - absorp.z))));
+        }
+
+        v3 wi;
+        imp_pdf = sample_bsdf_layered(B, wo, wi, thr, inside, rng, two_sided);
+
+        float survive = any_gt(thr, CRT_MIN_THROUGHPUT) ? 1.0f : 0.0f;
+        const bool rr_on = P.russian_roulette && depth >= 3;
+        if (rr_on) survive = minf(fmaf(0.0722f, thr.z, fmaf(0.7152f, thr.y, 0.2126f * thr.x)), 0.95f);
+        const bool dead = rand_float(rng) > survive || all_lt(thr, CRT_MIN_THROUGHPUT);
+        if (!dead && depth + 1 < P.max_depth) {
+          if (rr_on) thr = vscale(thr, 1.0f / survive);
+          dir = normalize3(from_local(wi, frame));
+          const float side = dot3(ng, dir) >= 0.0f ? eps : -eps;
+          org = vadd(vadd(org, vscale(dir, eps)), vscale(ng, side));
+          want_next = true;
+        }
+      }
+      rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
+      st.rad[slot] = rr;
+    }
+    // ---- warp-aggregated queue compaction
+    const uint32_t sh_at = warp_push(st.n_shadow + depth, want_shadow);
+    if (want_shadow) {
+      st.sh_o[sh_at] = make_float4(sh_o.x, sh_o.y, sh_o.z, sh_tmax);
+      st.sh_d[sh_at] = make_float4(sh_d.x, sh_d.y, sh_d.z, __uint_as_float(slot));
+      st.sh_c[sh_at] = make_float4(sh_c.x, sh_c.y, sh_c.z, 0.0f);
+    }
+    const uint32_t nx_at = warp_push(st.n_active + depth + 1, want_next);
+    if (want_next) {
+      qn[nx_at] = slot;
+      st.ray_o[slot] = make_float4(org.x, org.y, org.z, imp_pdf);
+      st.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float(inside ? 1 : 0));
+      st.thr[slot] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+    }
+  }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// SceneAnyHit for the shadow rays of this bounce; visible => add the contribution.
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
+{
+  const uint32_t n = st.n_shadow[depth];
+  Counters cnt = {};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 o = st.sh_o[i], d = st.sh_d[i];
+    Hit hit;
+    const bool occluded = traverse<true, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, hit, cnt);
+    if (COUNT) cnt.rays_any++;
+    if (!occluded) {
+      const uint32_t slot = __float_as_uint(d.w);
+      const float4 c = st.sh_c[i];
+      float4 r = st.rad[slot];
+      r.x += c.x; r.y += c.y; r.z += c.z;
+      st.rad[slot] = r;
+    }
+  }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// Accumulation: NaN -> 0, clamp, add the batch's samples of each pixel
+// in sample order (deterministic), count in .w.
+__global__ void __launch_bounds__(256)
+k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_batch, Counters* gcnt)
+{
+  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  for (uint32_t in = blockIdx.x * blockDim.x + threadIdx.x; in < per_sample; in += gridDim.x * blockDim.x) {
+    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
+    const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
+    if (px >= P.width || py >= P.height) continue;
+    float4 a = accum[(size_t)py * P.width + px];
+    for (uint32_t k = 0; k < n_batch; ++k) {
+      const float4 c = st.rad[(size_t)k * per_sample + in];
+      a.x += (c.x != c.x) ? 0.0f : minf(c.x, P.max_radiance);
+      a.y += (c.y != c.y) ? 0.0f : minf(c.y, P.max_radiance);
+      a.z += (c.z != c.z) ? 0.0f : minf(c.z, P.max_radiance);
+      a.w += 1.0f;
+    }
+    accum[(size_t)py * P.width + px] = a;
+  }
+  if (gcnt && blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&gcnt->samples, (unsigned long long)P.width * P.height * n_batch);
+}
+
+// Display.fs restated.
+__device__ __forceinline__ float filmic(float c)
+{
+  float f = fmaf(1.425f, c, 0.05f);
+  return (fmaf(c, f, 0.004f)) / (fmaf(c, f + 0.55f, 0.0491f)) - 0.0821f;
+}
+
+__global__ void __launch_bounds__(256)
+k_display(const float4* __restrict__ accum, uint32_t n_pixels, float exposure_scale, int tone_map, float wp_curve,
+          uint8_t* __restrict__ rgb8, float* __restrict__ rgb32f)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+    const float4 a = accum[i];
+    const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+    const float m[3] = { a.x * inv, a.y * inv, a.z * inv };
+    if (rgb32f) { rgb32f[3 * (size_t)i] = m[0]; rgb32f[3 * (size_t)i + 1] = m[1]; rgb32f[3 * (size_t)i + 2] = m[2]; }
+    if (rgb8) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x = m[c] * exposure_scale;
+        if (tone_map) x = filmic(x) / wp_curve;
+        x = sqrtf(maxf(x, 0.0f));
+        x = minf(x, 1.0f);
+        rgb8[3 * (size_t)i + c] = (uint8_t)(int)fmaf(x, 255.0f, 0.5f);
+      }
+    }
+  }
+}
+
+// Batch SceneNearestHit / SceneAnyHit on caller rays (parity hook crt_trace).
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128)
+k_trace(DeviceScene S, const float4* __restrict__ org, const float4* __restrict__ dir, uint32_t n,
+        float4* __restrict__ hit4, int32_t* __restrict__ hit_inst, Counters* gcnt)
+{
+  Counters cnt = {};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 o = org[i], d = dir[i];
+    Hit hit;
+    const bool f = traverse<ANY, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), d.w, hit, cnt);
+    if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
+    int32_t prim = -1;
+    if (f) prim = ANY ? 0 : __float_as_int(__ldg(S.tri_verts + 3 * (size_t)hit.tri).w);
+    hit4[i] = make_float4(hit.t, hit.u, hit.v, __int_as_float(prim));
+    if (hit_inst) hit_inst[i] = hit.inst;
+  }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+}  // namespace crt

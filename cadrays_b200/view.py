@@ -1,0 +1,429 @@
+"""Host-side mirror of the OCCT interface CADRays drives for this path.
+
+Same names, argument meaning and error behaviour as the reference call sites
+(file:line relative to the CADRays repository):
+
+  Graphic3d_Fresnel / Graphic3d_BSDF   src/Launcher/MaterialEditor.cxx:177-201,281-331
+  Graphic3d_RenderingParams            src/Launcher/SettingsWidget.cxx:65-90,217-229,263-478
+  V3d_View::Redraw / BufferDump        src/Launcher/AppViewer.cxx:1047,1259-1262; AppGui.cxx:345-350,430
+  V3d lights / SetTextureEnv           src/Launcher/LightSourcesEditor.cxx:242-369
+
+Everything computes in libcadrays_b200.so (sm_100a kernels); this file only
+marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, crt_bsdf, crt_camera, crt_light, crt_params, crt_stats
+
+# Graphic3d_RenderingMethod / Graphic3d_ToneMappingMethod / Graphic3d_BufferType
+Graphic3d_RM_RASTERIZATION = 0
+Graphic3d_RM_RAYTRACING = 1
+Graphic3d_ToneMappingMethod_Disabled = 0
+Graphic3d_ToneMappingMethod_Filmic = 1
+Graphic3d_BT_RGB = 0
+Graphic3d_BT_RGB_RayTraceHdrLeft = 1
+
+Graphic3d_FM_SCHLICK, Graphic3d_FM_CONSTANT, Graphic3d_FM_CONDUCTOR, Graphic3d_FM_DIELECTRIC = 0, 1, 2, 3
+
+
+def _clamp(x, lo, hi):
+    return min(max(float(x), lo), hi)
+
+
+class Graphic3d_Fresnel:
+    """Interface model of one BSDF layer; Serialize() is the vec4 the shader reads
+    (MaterialEditor.cxx:209-255, ImportExport.cxx:204-227)."""
+
+    def __init__(self, ftype: int, data: Sequence[float]):
+        self._type = ftype
+        self._data = tuple(float(v) for v in data)
+
+    @staticmethod
+    def CreateSchlick(r, g=None, b=None):
+        if g is None:
+            r, g, b = r
+        return Graphic3d_Fresnel(Graphic3d_FM_SCHLICK, (_clamp(r, 0, 1), _clamp(g, 0, 1), _clamp(b, 0, 1)))
+
+    @staticmethod
+    def CreateConstant(reflection):
+        return Graphic3d_Fresnel(Graphic3d_FM_CONSTANT, (0.0, _clamp(reflection, 0, 1), 0.0))
+
+    @staticmethod
+    def CreateConductor(n, k):
+        return Graphic3d_Fresnel(Graphic3d_FM_CONDUCTOR, (float(n), float(k), 0.0))
+
+    @staticmethod
+    def CreateDielectric(ior):
+        return Graphic3d_Fresnel(Graphic3d_FM_DIELECTRIC, (float(ior), 0.0, 0.0))
+
+    def FresnelType(self) -> int:
+        return self._type
+
+    def Serialize(self):
+        d = self._data
+        if self._type == Graphic3d_FM_SCHLICK:
+            return (d[0], d[1], d[2], 0.0)
+        if self._type == Graphic3d_FM_CONSTANT:
+            return (-1.0, 0.0, d[1], 0.0)
+        if self._type == Graphic3d_FM_CONDUCTOR:
+            return (-2.0, d[0], d[1], 0.0)
+        return (-3.0, d[0], 0.0, 0.0)
+
+
+@dataclass
+class Graphic3d_BSDF:
+    """The fields CADRays edits (MaterialEditor.cxx:294-331)."""
+    Kc: list = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])   # rgb + coat roughness
+    Kd: list = field(default_factory=lambda: [0.0, 0.0, 0.0])
+    Ks: list = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])   # rgb + base roughness
+    Kt: list = field(default_factory=lambda: [0.0, 0.0, 0.0])
+    Le: list = field(default_factory=lambda: [0.0, 0.0, 0.0])
+    Absorption: list = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])  # rgb colour + coefficient
+    FresnelCoat: Graphic3d_Fresnel = field(default_factory=lambda: Graphic3d_Fresnel.CreateConstant(0.0))
+    FresnelBase: Graphic3d_Fresnel = field(default_factory=lambda: Graphic3d_Fresnel.CreateConstant(1.0))
+
+    @staticmethod
+    def CreateDiffuse(weight):
+        return Graphic3d_BSDF(Kd=list(weight))
+
+    @staticmethod
+    def CreateMetallic(weight, fresnel: Graphic3d_Fresnel, roughness: float):
+        return Graphic3d_BSDF(Ks=[*weight, float(roughness)], FresnelBase=fresnel)
+
+    @staticmethod
+    def CreateTransparent(weight, absorption_color, absorption_coeff):
+        return Graphic3d_BSDF(Kt=list(weight), Absorption=[*absorption_color, float(absorption_coeff)])
+
+    @staticmethod
+    def CreateGlass(weight, absorption_color, absorption_coeff, ior):
+        b = Graphic3d_BSDF(Kt=list(weight), Absorption=[*absorption_color, float(absorption_coeff)])
+        b.Kc = [1.0, 1.0, 1.0, 0.0]
+        b.FresnelCoat = Graphic3d_Fresnel.CreateDielectric(ior)
+        return b
+
+    def Normalize(self):
+        """CADRays' clamp + base-layer normalisation (MaterialEditor.cxx:294-329)."""
+        for v in (self.Kc, self.Kd, self.Ks, self.Kt, self.Absorption):
+            for k in range(3):
+                v[k] = _clamp(v[k], 0.0, 1.0)
+        for k in range(3):
+            self.Le[k] = max(float(self.Le[k]), 0.0)
+        self.Absorption[3] = max(float(self.Absorption[3]), 0.0)
+        mx = max(self.Kd[k] + self.Ks[k] + self.Kt[k] for k in range(3))
+        if mx > 1.0:
+            for k in range(3):
+                self.Kd[k] /= mx
+                self.Ks[k] /= mx
+                self.Kt[k] /= mx
+        return self
+
+    def to_c(self) -> crt_bsdf:
+        c = crt_bsdf()
+        c.Kc[:] = self.Kc
+        c.Kd[:] = [*self.Kd, 0.0]
+        c.Ks[:] = self.Ks
+        c.Kt[:] = [*self.Kt, 0.0]
+        c.Le[:] = [*self.Le, 0.0]
+        c.FresnelCoat[:] = self.FresnelCoat.Serialize()
+        c.FresnelBase[:] = self.FresnelBase.Serialize()
+        c.Absorption[:] = self.Absorption
+        return c
+
+
+@dataclass
+class Graphic3d_RenderingParams:
+    """Fields of Graphic3d_RenderingParams that CADRays sets."""
+    Method: int = Graphic3d_RM_RAYTRACING
+    IsGlobalIlluminationEnabled: bool = True
+    RaytracingDepth: int = 8
+    SamplesPerPixel: int = 1
+    RadianceClampingValue: float = 50.0
+    TwoSidedBsdfModels: bool = False
+    CoherentPathTracingMode: bool = False
+    AdaptiveScreenSampling: bool = False        # not implemented
+    ToneMappingMethod: int = Graphic3d_ToneMappingMethod_Disabled
+    WhitePoint: float = 1.0
+    Exposure: float = 0.0
+    CameraApertureRadius: float = 0.0
+    CameraFocalPlaneDist: float = 1.0
+    UseEnvironmentMapBackground: bool = True
+    # not OCCT fields: generator seed, roulette switch, background colour, wave size
+    FrameSeed: int = 1
+    RussianRoulette: bool = True
+    BackgroundColor: tuple = (0.0, 0.0, 0.0)
+    SamplesPerBatch: int = 0
+
+    def to_c(self) -> crt_params:
+        if self.Method != Graphic3d_RM_RAYTRACING or not self.IsGlobalIlluminationEnabled:
+            raise ValueError("only Graphic3d_RM_RAYTRACING with IsGlobalIlluminationEnabled is implemented "
+                             "(the path-traced mode CADRays calls 'GI', SettingsWidget.cxx:76-84)")
+        if self.AdaptiveScreenSampling:
+            raise ValueError("AdaptiveScreenSampling is not implemented")
+        p = crt_params()
+        p.max_depth = int(self.RaytracingDepth)
+        p.max_radiance = float(self.RadianceClampingValue)
+        p.two_sided = int(self.TwoSidedBsdfModels)
+        p.coherent_rng = int(self.CoherentPathTracingMode)
+        p.aperture_radius = float(self.CameraApertureRadius)
+        p.focal_dist = float(self.CameraFocalPlaneDist)
+        p.tone_map = int(self.ToneMappingMethod)
+        p.white_point = float(self.WhitePoint)
+        p.exposure = float(self.Exposure)
+        p.env_as_background = int(self.UseEnvironmentMapBackground)
+        p.frame_seed0 = int(self.FrameSeed) & 0xFFFFFFFF
+        p.russian_roulette = int(self.RussianRoulette)
+        p.background[:] = [float(v) for v in self.BackgroundColor]
+        p.samples_per_batch = int(self.SamplesPerBatch)
+        return p
+
+
+@dataclass
+class Graphic3d_Camera:
+    Eye: tuple = (0.0, -3.0, 0.0)
+    Direction: tuple = (0.0, 1.0, 0.0)
+    Up: tuple = (0.0, 0.0, 1.0)
+    FOVy: float = 45.0
+    Aspect: float = 1.0
+    IsOrthographic: bool = False
+    Scale: float = 1.0
+
+    def to_c(self) -> crt_camera:
+        c = crt_camera()
+        c.eye[:] = [float(v) for v in self.Eye]
+        c.dir[:] = [float(v) for v in self.Direction]
+        c.up[:] = [float(v) for v in self.Up]
+        c.fovy_deg = float(self.FOVy)
+        c.aspect = float(self.Aspect)
+        c.is_ortho = int(self.IsOrthographic)
+        c.ortho_scale = float(self.Scale)
+        return c
+
+
+def make_light(is_point: bool, posdir, color=(1.0, 1.0, 1.0), intensity=1.0, smoothness=0.0) -> crt_light:
+    """V3d_PositionalLight / V3d_DirectionalLight (LightSourcesEditor.cxx:242-310)."""
+    l = crt_light()
+    l.emission[:] = [float(c) * float(intensity) for c in color]
+    l.smoothness = float(smoothness)
+    l.posdir[:] = [float(v) for v in posdir]
+    l.is_point = int(bool(is_point))
+    return l
+
+
+def _fptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class V3d_View:
+    """One render target on one GPU: owns a crt_context."""
+
+    def __init__(self, device: int = 0, host_only: bool = False):
+        self._lib = _ffi.load_library()
+        self._ctx = C.c_void_p()
+        if host_only:
+            check(self._lib.crt_create_host_only(C.byref(self._ctx)))
+        else:
+            check(self._lib.crt_create(int(device), C.byref(self._ctx)))
+        self._params = Graphic3d_RenderingParams()
+        self._camera = Graphic3d_Camera()
+        self._size = (0, 0)
+        self.device = device
+
+    # -- lifetime
+    def Remove(self):
+        if self._ctx:
+            self._lib.crt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Remove()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    # -- scene (AIS Display of a triangulation with a location and a material aspect)
+    def AddMesh(self, pos, idx, nrm=None, uv=None) -> int:
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
+        nrm = None if nrm is None else np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        out = C.c_uint32()
+        check(self._lib.crt_mesh_create(self._ctx, _fptr(pos), _fptr(nrm), _fptr(uv), pos.shape[0],
+                                        idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.shape[0], C.byref(out)))
+        return out.value
+
+    def Display(self, mesh_id: int, trsf=None, material_id: int = 0) -> int:
+        xf = None if trsf is None else np.ascontiguousarray(trsf, dtype=np.float32).reshape(12)
+        out = C.c_uint32()
+        check(self._lib.crt_instance_add(self._ctx, int(mesh_id), _fptr(xf), int(material_id), C.byref(out)))
+        return out.value
+
+    def SetLocation(self, inst_id: int, trsf):
+        xf = np.ascontiguousarray(trsf, dtype=np.float32).reshape(12)
+        check(self._lib.crt_instance_set_transform(self._ctx, int(inst_id), _fptr(xf)))
+
+    def SetMaterialIndex(self, inst_id: int, material_id: int):
+        check(self._lib.crt_instance_set_material(self._ctx, int(inst_id), int(material_id)))
+
+    def Clear(self):
+        check(self._lib.crt_scene_clear(self._ctx))
+
+    def SetMaterials(self, bsdfs: Sequence):
+        arr = (crt_bsdf * max(len(bsdfs), 1))()
+        for i, b in enumerate(bsdfs):
+            arr[i] = b.to_c() if isinstance(b, Graphic3d_BSDF) else b
+        check(self._lib.crt_materials_set(self._ctx, arr, len(bsdfs)))
+
+    def SetLights(self, lights: Sequence[crt_light]):
+        arr = (crt_light * max(len(lights), 1))()
+        for i, l in enumerate(lights):
+            arr[i] = l
+        check(self._lib.crt_lights_set(self._ctx, arr, len(lights)))
+
+    def SetTextureEnv(self, image: Optional[np.ndarray]):
+        """Lat-long environment map: uint8 (h,w,3) is linearised as (c/255)^2, float32 is linear."""
+        if image is None:
+            check(self._lib.crt_envmap_set_rgb32f(self._ctx, None, 0, 0))
+            return
+        h, w = image.shape[:2]
+        if image.dtype == np.uint8:
+            a = np.ascontiguousarray(image[..., :3])
+            check(self._lib.crt_envmap_set_rgb8(self._ctx, a.ctypes.data_as(C.POINTER(C.c_uint8)), w, h))
+        else:
+            a = np.ascontiguousarray(image[..., :3], dtype=np.float32)
+            check(self._lib.crt_envmap_set_rgb32f(self._ctx, _fptr(a), w, h))
+
+    # -- parameters
+    def ChangeRenderingParams(self) -> Graphic3d_RenderingParams:
+        return self._params
+
+    def SetRenderingParams(self, p: Graphic3d_RenderingParams):
+        self._params = p
+        cp = p.to_c()
+        check(self._lib.crt_params_set(self._ctx, C.byref(cp)))
+
+    def Camera(self) -> Graphic3d_Camera:
+        return self._camera
+
+    def SetCamera(self, cam: Graphic3d_Camera):
+        self._camera = cam
+        cc = cam.to_c()
+        check(self._lib.crt_camera_set(self._ctx, C.byref(cc)))
+
+    def SetWindowSize(self, width: int, height: int):
+        check(self._lib.crt_resize(self._ctx, int(width), int(height)))
+        self._size = (int(width), int(height))
+
+    def Update(self):
+        """Explicit form of OCCT's state-counter invalidation: BVH (re)build + upload."""
+        check(self._lib.crt_commit(self._ctx))
+
+    # -- render
+    def Redraw(self, samples: Optional[int] = None) -> int:
+        """V3d_View::Redraw(): adds SamplesPerPixel samples (or `samples`); returns the total."""
+        n = int(self._params.SamplesPerPixel if samples is None else samples)
+        total = C.c_uint64()
+        check(self._lib.crt_render(self._ctx, n, C.byref(total)))
+        return total.value
+
+    def RedrawAsync(self, samples: int):
+        check(self._lib.crt_render_async(self._ctx, int(samples)))
+
+    def Sync(self):
+        check(self._lib.crt_sync(self._ctx))
+
+    def ResetAccumulation(self, first_sample: int = 0):
+        check(self._lib.crt_reset_accumulation(self._ctx, int(first_sample)))
+
+    def SetNextSample(self, index: int):
+        check(self._lib.crt_set_next_sample(self._ctx, int(index)))
+
+    def BufferDump(self, buffer_type: int = Graphic3d_BT_RGB, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Graphic3d_CView::BufferDump: RGB8 (tone-mapped) or float RGB (mean radiance), bottom-up rows."""
+        w, h = self._size
+        if buffer_type == Graphic3d_BT_RGB:
+            img = out if out is not None else np.empty((h, w, 3), dtype=np.uint8)
+            check(self._lib.crt_read_ldr(self._ctx, img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
+        else:
+            img = out if out is not None else np.empty((h, w, 3), dtype=np.float32)
+            check(self._lib.crt_read_hdr(self._ctx, _fptr(img), 0))
+        return img
+
+    def AccumDevicePtr(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        check(self._lib.crt_accum_device_ptr(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def BindAccum(self, device_ptr: Optional[int], nbytes: int = 0):
+        check(self._lib.crt_accum_bind(self._ctx, C.c_void_p(device_ptr) if device_ptr else None, nbytes))
+
+    def DumpFrom(self, device_ptr: int) -> np.ndarray:
+        w, h = self._size
+        img = np.empty((h, w, 3), dtype=np.uint8)
+        check(self._lib.crt_read_ldr_from(self._ctx, C.c_void_p(device_ptr), img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
+        return img
+
+    # -- parity hooks
+    def Trace(self, org, dir, tmax=None, any_hit: bool = False):
+        org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
+        dir = np.ascontiguousarray(dir, dtype=np.float32).reshape(-1, 3)
+        n = org.shape[0]
+        tm = None if tmax is None else np.ascontiguousarray(tmax, dtype=np.float32).reshape(n)
+        prim = np.empty(n, np.int32); inst = np.empty(n, np.int32)
+        t = np.empty(n, np.float32); u = np.empty(n, np.float32); v = np.empty(n, np.float32)
+        ip = C.POINTER(C.c_int32)
+        check(self._lib.crt_trace(self._ctx, _fptr(org), _fptr(dir), _fptr(tm), n, int(any_hit),
+                                  prim.ctypes.data_as(ip), inst.ctypes.data_as(ip), _fptr(t), _fptr(u), _fptr(v)))
+        return prim, inst, t, u, v
+
+    def TraceDevice(self, org4_ptr: int, dir4_ptr: int, n: int, hit4_ptr: int, inst_ptr: int = 0, any_hit: bool = False):
+        check(self._lib.crt_trace_device(self._ctx, C.c_void_p(org4_ptr), C.c_void_p(dir4_ptr), int(n), int(any_hit),
+                                         C.c_void_p(hit4_ptr), C.c_void_p(inst_ptr) if inst_ptr else None))
+
+    def ExportBVH(self) -> bytes:
+        n = C.c_size_t()
+        check(self._lib.crt_bvh_export(self._ctx, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        check(self._lib.crt_bvh_export(self._ctx, buf, n.value, C.byref(n)))
+        return buf.raw
+
+    def ImportBVH(self, blob: bytes):
+        check(self._lib.crt_bvh_import(self._ctx, blob, len(blob)))
+
+    # -- metrics
+    def EnableStats(self, on: bool = True):
+        check(self._lib.crt_stats_enable(self._ctx, int(on)))
+
+    def ResetStats(self):
+        check(self._lib.crt_stats_reset(self._ctx))
+
+    def Stats(self) -> dict:
+        s = crt_stats()
+        check(self._lib.crt_stats_get(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def EnableTiming(self, on: bool = True):
+        check(self._lib.crt_timing_enable(self._ctx, int(on)))
+
+    def Timing(self):
+        ms = (C.c_double * 6)()
+        ln = (C.c_uint64 * 6)()
+        check(self._lib.crt_timing_get(self._ctx, ms, ln))
+        names = ("generate", "extend", "shade", "connect", "resolve", "render")
+        return {n: (ms[i], int(ln[i])) for i, n in enumerate(names)}
+
+    def Stream(self) -> int:
+        p = C.c_void_p()
+        check(self._lib.crt_stream(self._ctx, C.byref(p)))
+        return p.value or 0

@@ -1,0 +1,305 @@
+"""GPU parity tests proper: the sm_100a path (through the C-ABI) against the CPU oracle.
+
+Three levels of BASELINE.json's north_star, all measured against OUR CPU restatement
+(parity with OCCT itself is unpinned -- see oracle/cadrays_oracle.h):
+  level 1  closest-hit primitive ids on identical ray batches   -> bit-exact (t,u,v too)
+  level 2  single-sample radiance with the RNG reproduced       -> bit-exact (bound stated: 1e-4)
+  level 3  converged images                                     -> bit-exact at equal spp
+"""
+import numpy as np
+import pytest
+
+from cadrays_b200 import scenes
+from cadrays_b200._ffi import CRT_ERR_INVALID_ARG, CRT_ERR_STATE, CrtError
+from cadrays_b200.view import (Graphic3d_BT_RGB, Graphic3d_BT_RGB_RayTraceHdrLeft, Graphic3d_BSDF,
+                               Graphic3d_RenderingParams, Graphic3d_ToneMappingMethod_Filmic, V3d_View, make_light)
+
+pytestmark = pytest.mark.gpu
+
+LEVEL2_TOL = 1e-4   # north_star: "single-sample radiance ... matches within 1e-4"
+
+
+def _pair(desc):
+    """Product view on cuda:0 + oracle on the SAME exported BVH bytes."""
+    from oracle.oracle_ffi import OracleScene
+    view = V3d_View(0)
+    desc.apply(view)
+    orc = OracleScene(view.ExportBVH())
+    orc.configure(desc)
+    return view, orc
+
+
+def _small_assembly():
+    return scenes.assembly(n_parts=64, target_tris=40_000, seed=2, width=160, height=96, depth=6)
+
+
+def _small_instanced():
+    return scenes.instanced(n_inst=48, n_meshes=4, seed=5, width=160, height=96, depth=5, nu=24, nv=13)
+
+
+SCENES = {
+    "cornell": lambda: scenes.cornell_box(128, 128, depth=5, sphere_res=(32, 16)),
+    "assembly": _small_assembly,
+    "instanced": _small_instanced,
+    "materials": lambda: scenes.materials_scene(160, 96, depth=8, sphere_res=(32, 16)),
+}
+
+
+@pytest.fixture(scope="module", params=list(SCENES))
+def pair(request, product_lib, oracle_lib):
+    desc = SCENES[request.param]()
+    view, orc = _pair(desc)
+    yield desc, view, orc
+    view.Remove()
+    orc.close()
+
+
+def _scene_box(orc_blob_view):
+    import struct
+    hdr = struct.unpack_from("<8I7f", orc_blob_view, 0)
+    return np.array(hdr[8:11]), np.array(hdr[11:14])
+
+
+# ------------------------------------------------------------------ level 1
+
+def test_level1_closest_hit_bit_exact(pair):
+    desc, view, orc = pair
+    lo, hi = _scene_box(view.ExportBVH())
+    org, d = scenes.random_rays(200_000, lo, hi, seed=11)
+    g = view.Trace(org, d)
+    o = orc.trace(org, d)
+    ties = int(np.sum((g[0] != o[0]) & (g[2] == o[2])))
+    assert np.array_equal(g[0], o[0]), f"primitive ids differ on {np.sum(g[0] != o[0])} rays ({ties} exact-distance ties)"
+    assert np.array_equal(g[1], o[1])
+    hit = g[0] >= 0
+    assert hit.sum() > 1000
+    # t within 1e-6 relative is the stated bar; we get bit equality
+    assert np.array_equal(g[2], o[2]) and np.array_equal(g[3][hit], o[3][hit]) and np.array_equal(g[4][hit], o[4][hit])
+    rel = np.abs(g[2][hit] - o[2][hit]) / np.maximum(o[2][hit], 1e-30)
+    assert rel.max() <= 1e-6
+
+
+def test_level1_any_hit_and_tmax(pair):
+    desc, view, orc = pair
+    lo, hi = _scene_box(view.ExportBVH())
+    org, d = scenes.random_rays(100_000, lo, hi, seed=12)
+    tmax = np.random.default_rng(3).uniform(0.01, float(np.linalg.norm(hi - lo)), size=org.shape[0]).astype(np.float32)
+    g = view.Trace(org, d, tmax, any_hit=True)
+    o = orc.trace(org, d, tmax, any_hit=True)
+    assert np.array_equal(g[0], o[0])
+    # any-hit must agree with closest-hit: occluded iff the closest hit is nearer than tmax
+    n = view.Trace(org, d, tmax, any_hit=False)
+    assert np.array_equal(g[0] == 0, n[0] >= 0)
+
+
+def test_level1_work_counters_match(pair):
+    desc, view, orc = pair
+    lo, hi = _scene_box(view.ExportBVH())
+    org, d = scenes.random_rays(50_000, lo, hi, seed=13)
+    view.EnableStats(True)
+    view.ResetStats()
+    view.Trace(org, d)
+    gs = view.Stats()
+    view.EnableStats(False)
+    os_ = orc.trace(org, d, stats=True)[5]
+    for k in ("rays_nearest", "n_inner", "n_leaf", "n_tri", "n_switch"):
+        assert gs[k] == os_[k], k
+
+
+def test_level1_degenerate_rays(product_lib, oracle_lib):
+    desc = SCENES["cornell"]()
+    view, orc = _pair(desc)
+    org = np.array([[0.5, -1, 0.5], [0.5, -1, 0.5], [np.nan, 0, 0], [0.5, 0.5, 0.5], [0.5, -1, 0.5]], np.float32)
+    d = np.array([[0, 0, 0], [np.nan, 1, 0], [0, 1, 0], [0, 0, 1], [0, 1, 0]], np.float32)
+    g = view.Trace(org, d)
+    o = orc.trace(org, d)
+    assert np.array_equal(g[0], o[0]) and list(g[0][:3]) == [-1, -1, -1] and g[0][3] >= 0 and g[0][4] >= 0
+    # zero rays is a no-op
+    view.Trace(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    view.Remove()
+
+
+def test_empty_scene_misses(product_lib, oracle_lib):
+    view = V3d_View(0)
+    view.SetWindowSize(16, 16)
+    view.Update()
+    g = view.Trace(np.zeros((4, 3), np.float32), np.tile(np.array([[0, 0, 1]], np.float32), (4, 1)))
+    assert (g[0] == -1).all()
+    view.Redraw(2)
+    img = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    assert np.all(img == 0)
+    view.Remove()
+
+
+# ------------------------------------------------------------------ level 2 / 3
+
+def _bound_accum(view):
+    """Binds a torch tensor as the float4 SUM buffer (the NCCL all-reduce path) and returns it."""
+    import torch
+    w, h = view._size
+    t = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    view.BindAccum(t.data_ptr(), t.numel() * 4)
+    return t
+
+
+def test_level2_single_sample_radiance(pair):
+    desc, view, orc = pair
+    view.ResetAccumulation(0)
+    view.Redraw(1)
+    g = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    o = orc.hdr(orc.render(desc.width, desc.height, 1))
+    assert np.isfinite(g).all()
+    assert g.max() > 0
+    err = np.abs(g - o)
+    assert err.max() <= LEVEL2_TOL, f"max abs radiance error {err.max()} on {np.sum(err > LEVEL2_TOL)} values"
+    assert np.array_equal(g, o), "single-sample radiance is expected to be bit-exact"
+
+
+def test_level3_accumulated_image(pair):
+    desc, view, orc = pair
+    spp = 24
+    view.ResetAccumulation(0)
+    view.Redraw(5)          # uneven call pattern: batching must not change the result
+    view.Redraw(spp - 5)
+    g = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    acc = orc.render(desc.width, desc.height, spp)
+    o = orc.hdr(acc)
+    rmse = float(np.sqrt(np.mean((g - o) ** 2)))
+    assert rmse <= 1e-6 * max(1.0, float(o.mean())), rmse
+    assert np.array_equal(g, o)
+    # Display.fs: tone-mapped RGB8
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB), orc.display(acc))
+
+
+def test_sample_partition_union(pair):
+    """Two 'ranks' rendering disjoint sample ranges sum to the single-range image (float order aside)."""
+    desc, view, orc = pair
+    spp = 8
+    t = _bound_accum(view)
+    view.ResetAccumulation(0)
+    view.Redraw(spp)
+    full = t.cpu().numpy().copy()
+    view.ResetAccumulation(0)
+    view.Redraw(spp // 2)
+    a = t.cpu().numpy().copy()
+    view.ResetAccumulation(spp // 2)
+    view.Redraw(spp // 2)
+    b = t.cpu().numpy().copy()
+    view.BindAccum(None)
+    assert full[..., 3].min() == spp
+    assert np.allclose(a + b, full, rtol=1e-5, atol=1e-6)
+    assert np.array_equal((a + b)[..., 3], full[..., 3])
+    # the bound buffer holds what the internal one would: compare with the oracle's sums
+    o = orc.render(desc.width, desc.height, spp)
+    assert np.array_equal(full, o)
+    view.ResetAccumulation(0)
+
+
+@pytest.mark.parametrize("variant", ["two_sided", "aperture", "coherent", "filmic", "no_rr", "env", "env_hidden"])
+def test_level2_parameter_variants(variant, product_lib, oracle_lib):
+    desc = scenes.cornell_box(96, 96, depth=5, sphere_res=(24, 12))
+    p = desc.params
+    if variant == "two_sided":
+        p.TwoSidedBsdfModels = True
+    elif variant == "aperture":
+        p.CameraApertureRadius, p.CameraFocalPlaneDist = 0.05, 1.6
+    elif variant == "coherent":
+        p.CoherentPathTracingMode = True
+    elif variant == "filmic":
+        p.ToneMappingMethod, p.WhitePoint, p.Exposure = Graphic3d_ToneMappingMethod_Filmic, 2.0, 0.7
+    elif variant == "no_rr":
+        p.RussianRoulette = False
+    elif variant in ("env", "env_hidden"):
+        g = np.random.default_rng(5)
+        env = (g.random((16, 32, 3)) * 255).astype(np.uint8) if variant == "env" else g.random((16, 32, 3)).astype(np.float32) * 3
+        desc.envmap = env
+        desc.lights = []
+        desc.instances = desc.instances[:3] + desc.instances[5:]   # open the box: drop ceiling and floor
+        p.UseEnvironmentMapBackground = variant == "env"
+        p.BackgroundColor = (0.1, 0.2, 0.3)
+    view, orc = _pair(desc)
+    view.Redraw(3)
+    acc = orc.render(desc.width, desc.height, 3)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc))
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB), orc.display(acc))
+    view.Remove()
+
+
+def test_lights_variants(product_lib, oracle_lib):
+    """Delta lights (smoothness 0), several lights, directional + positional mix."""
+    desc = scenes.cornell_box(96, 96, depth=4, sphere_res=(24, 12))
+    desc.lights = [make_light(True, (0.5, 0.5, 0.85), intensity=2.0, smoothness=0.0),
+                   make_light(False, (0.2, 0.5, -1.0), color=(1, 0.9, 0.8), intensity=3.0, smoothness=0.0),
+                   make_light(False, (-0.3, 0.4, -0.8), intensity=5.0, smoothness=0.2),
+                   make_light(True, (0.2, 0.3, 0.6), color=(0.2, 1, 0.2), intensity=30.0, smoothness=0.03)]
+    view, orc = _pair(desc)
+    view.Redraw(4)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(orc.render(desc.width, desc.height, 4)))
+    view.Remove()
+
+
+def test_ragged_resolution_and_material_default(product_lib, oracle_lib):
+    """Width/height that are not multiples of the 8x4 warp tile; instance with an out-of-range material id."""
+    desc = scenes.cornell_box(101, 67, depth=4, sphere_res=(16, 8))
+    m, xf, _ = desc.instances[6]
+    desc.instances[6] = (m, xf, 9999)
+    view, orc = _pair(desc)
+    view.Redraw(2)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(orc.render(101, 67, 2)))
+    view.Remove()
+
+
+def test_bvh_import_roundtrip(product_lib, oracle_lib):
+    desc = SCENES["cornell"]()
+    view, orc = _pair(desc)
+    blob = view.ExportBVH()
+    other = V3d_View(0)
+    other.ImportBVH(blob)
+    org, d = scenes.random_rays(20_000, (0, 0, 0), (1, 1, 1), seed=4)
+    a, b = view.Trace(org, d), other.Trace(org, d)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(CrtError):
+        other.ImportBVH(blob[:100])
+    view.Remove(); other.Remove()
+
+
+def test_error_behaviour(product_lib):
+    view = V3d_View(0)
+    with pytest.raises(CrtError) as e:
+        view.Redraw(1)
+    assert e.value.code == CRT_ERR_STATE
+    with pytest.raises(CrtError) as e:
+        view.Display(5)
+    assert e.value.code == CRT_ERR_INVALID_ARG
+    with pytest.raises(CrtError):
+        view.AddMesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 7]], np.uint32))
+    with pytest.raises(CrtError):
+        view.SetWindowSize(0, 10)
+    view.Remove()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config C2)
+
+def test_full_size_properties(product_lib):
+    """1080p, depth 8, ~1M triangles: size-independent properties where the oracle is too slow."""
+    desc = scenes.assembly()           # config C2
+    assert abs(desc.n_triangles() - 1_000_000) <= 10_000 + 2
+    view = V3d_View(0)
+    desc.apply(view)
+    view.Redraw(2)
+    a = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft).copy()
+    assert np.isfinite(a).all() and a.max() > 0 and (a >= 0).all()
+    view.ResetAccumulation(0)
+    view.Redraw(2)
+    b = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    assert np.array_equal(a, b), "rendering must be deterministic"
+    # any-hit agrees with closest-hit on 1M random rays
+    import struct
+    hdr = struct.unpack_from("<8I7f", view.ExportBVH(), 0)
+    org, d = scenes.random_rays(1_000_000, hdr[8:11], hdr[11:14], seed=21)
+    n = view.Trace(org, d)
+    s = view.Trace(org, d, any_hit=True)
+    assert np.array_equal(n[0] >= 0, s[0] == 0)
+    view.Remove()
