@@ -1,0 +1,214 @@
+"""CPU tests of the product's host side (no GPU, no compute calls): the C-ABI library loads and
+exports every symbol include/cadrays_b200.h declares, the host BVH builder produces a well-formed
+two-level tree, the host mirror keeps CADRays' material semantics, and device entry points fail
+loudly without a device."""
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from cadrays_b200 import _ffi, scenes
+from cadrays_b200._ffi import CRT_ERR_INVALID_ARG, CRT_ERR_NO_DEVICE, CRT_ERR_STATE, CrtError
+from cadrays_b200.view import (Graphic3d_BSDF, Graphic3d_Fresnel, Graphic3d_RenderingParams, V3d_View)
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    header = (REPO / "include" / "cadrays_b200.h").read_text()
+    declared = set(re.findall(r"\b(crt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"crt_bsdf", "crt_light", "crt_params", "crt_camera", "crt_stats", "crt_context", "crt_status"}
+    assert len(declared) >= 35
+    for name in sorted(declared):
+        assert hasattr(product_lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_ffi.PROTOTYPES), "ctypes prototypes and header disagree"
+    assert product_lib.crt_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    assert C.sizeof(_ffi.crt_bsdf) == 128
+    assert C.sizeof(_ffi.crt_light) == 32
+    assert C.sizeof(_ffi.crt_stats) == 96
+    assert C.sizeof(_ffi.crt_camera) == 52
+    assert C.sizeof(_ffi.crt_params) == 64
+
+
+def test_no_device_fails_loudly(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(CrtError) as e:
+        V3d_View(0)
+    assert e.value.code == CRT_ERR_NO_DEVICE
+    assert "no CPU fallback" in e.value.message
+    v = V3d_View(host_only=True)
+    scenes.cornell_box(32, 32, sphere_res=(8, 4)).apply(v, with_target=False)
+    for call in (lambda: v.Redraw(1), lambda: v.SetWindowSize(8, 8),
+                 lambda: v.Trace(np.zeros((1, 3), np.float32), np.ones((1, 3), np.float32)),
+                 lambda: v.ImportBVH(v.ExportBVH())):
+        with pytest.raises(CrtError) as e:
+            call()
+        assert e.value.code in (CRT_ERR_NO_DEVICE, CRT_ERR_STATE)
+    v.Remove()
+
+
+def test_product_never_imports_the_oracle():
+    """No include, import, link or dlopen of anything under oracle/ from the product tree."""
+    bad = re.compile(r"(#\s*include[^\n]*oracle|^\s*(from|import)\s+oracle|oracle_ffi|libcadrays_oracle|dlopen)", re.M)
+    files = list((REPO / "cadrays_b200").rglob("*.py")) + [p for p in (REPO / "cadrays_b200" / "csrc").glob("*") if p.is_file()]
+    files.append(REPO / "include" / "cadrays_b200.h")
+    for p in files:
+        m = bad.search(p.read_text(errors="ignore"))
+        assert m is None, (p, m.group(0))
+    from cadrays_b200 import build
+    assert not any("oracle" in str(x) for x in build._sources())
+
+
+def _parse_blob(blob):
+    h = struct.unpack_from("<8I7fI", blob, 0)
+    hdr = dict(zip(("magic", "version", "n_nodes", "n_verts", "n_tris", "n_inst", "n_top", "flags"), h[:8]))
+    hdr["min"], hdr["max"], hdr["eps"] = np.array(h[8:11]), np.array(h[11:14]), h[14]
+    off = 64
+    def take(dtype, count, width):
+        nonlocal off
+        a = np.frombuffer(blob, dtype=dtype, count=count * width, offset=off).reshape(count, width)
+        off = (off + a.nbytes + 15) & ~15
+        return a
+    n, v, t, i = hdr["n_nodes"], hdr["n_verts"], hdr["n_tris"], hdr["n_inst"]
+    out = dict(hdr=hdr, info=take(np.int32, n, 4), bmin=take(np.float32, n, 3), bmax=take(np.float32, n, 3),
+               pos=take(np.float32, v, 3), nrm=take(np.float32, v, 3), uv=take(np.float32, v, 2),
+               tris=take(np.int32, t, 4), inv=take(np.float32, i, 16), meta=take(np.int32, i, 4))
+    assert off <= len(blob)
+    return out
+
+
+@pytest.mark.parametrize("which", ["cornell", "assembly", "instanced"])
+def test_bvh_blob_is_well_formed(which, product_lib):
+    desc = {"cornell": lambda: scenes.cornell_box(32, 32, sphere_res=(24, 12)),
+            "assembly": lambda: scenes.assembly(n_parts=40, target_tris=20000, width=32, height=32),
+            "instanced": lambda: scenes.instanced(n_inst=30, n_meshes=3, width=32, height=32, nu=16, nv=9)}[which]()
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    b = _parse_blob(v.ExportBVH())
+    v.Remove()
+    hdr = b["hdr"]
+    assert hdr["magic"] == 0x42545243 and hdr["version"] == 1 and hdr["n_inst"] == len(desc.instances)
+    assert hdr["eps"] == pytest.approx(max(1e-6, 1e-4 * float(np.linalg.norm(hdr["max"] - hdr["min"]))), rel=1e-5)
+    info, bmin, bmax = b["info"], b["bmin"], b["bmax"]
+    seen_inst = set()
+    # top level: leaf size 1, every instance exactly once, child boxes inside the parent's
+    stack = [(0, 0)]
+    while stack:
+        n, depth = stack.pop()
+        assert depth <= 32
+        x, y, z, w = info[n]
+        if x == 0:
+            for c in (y, z):
+                assert (bmin[c] >= bmin[n] - 1e-6).all() and (bmax[c] <= bmax[n] + 1e-6).all()
+                stack.append((c, depth + 1))
+        else:
+            assert x > 0 and x - 1 not in seen_inst
+            seen_inst.add(x - 1)
+            assert b["meta"][x - 1][2] == y
+    assert seen_inst == set(range(hdr["n_inst"]))
+    # bottom level, per distinct mesh: leaves partition the triangle range, leaf size <= 5,
+    # every triangle inside its leaf box, children inside parents
+    for root, voff, toff in {(r[1], r[2], r[3]) for r in info[:hdr["n_top"]] if r[0] > 0}:
+        covered = []
+        stack = [(root, 0)]
+        while stack:
+            n, depth = stack.pop()
+            assert depth <= 32
+            x, y, z, w = info[n]
+            if x == 0:
+                for c in (root + y, root + z):
+                    assert (bmin[c] >= bmin[n] - 1e-6).all() and (bmax[c] <= bmax[n] + 1e-6).all()
+                    stack.append((c, depth + 1))
+            else:
+                assert x < 0 and 0 < z - y + 1 <= 5
+                for k in range(y, z + 1):
+                    tri = b["tris"][toff + k]
+                    p = b["pos"][voff + tri[:3]]
+                    assert (p >= bmin[n] - 1e-6).all() and (p <= bmax[n] + 1e-6).all()
+                    covered.append(k)
+        covered.sort()
+        assert covered == list(range(len(covered)))
+    # inverse matrices really invert the instance transforms
+    for k, (m, xf, mat) in enumerate(desc.instances):
+        M = np.eye(4); M[:3] = np.eye(3, 4) if xf is None else xf
+        Minv = b["inv"][k].reshape(4, 4)
+        assert np.allclose(Minv @ M, np.eye(4), atol=1e-4)
+        assert b["meta"][k][0] == mat
+
+
+def test_builder_rejects_bad_input(product_lib):
+    v = V3d_View(host_only=True)
+    with pytest.raises(CrtError) as e:
+        v.AddMesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 3]], np.uint32))
+    assert e.value.code == CRT_ERR_INVALID_ARG
+    with pytest.raises(CrtError):
+        v.AddMesh(np.array([[0, 0, np.inf], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    m = v.AddMesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    v.Display(m, np.zeros((3, 4), np.float32))          # singular transform
+    with pytest.raises(CrtError) as e:
+        v.Update()
+    assert e.value.code == CRT_ERR_INVALID_ARG
+    with pytest.raises(CrtError) as e:
+        V3d_View(host_only=True).ExportBVH()              # export before commit
+    assert e.value.code == CRT_ERR_STATE
+    v.Remove()
+
+
+def test_empty_and_single_triangle_scenes(product_lib, oracle_lib):
+    from oracle.oracle_ffi import OracleScene
+    v = V3d_View(host_only=True)
+    v.Update()
+    b = _parse_blob(v.ExportBVH())
+    assert b["hdr"]["n_nodes"] == 0 and b["hdr"]["n_inst"] == 0
+    o = OracleScene(v.ExportBVH())
+    assert o.trace(np.zeros((2, 3), np.float32), np.ones((2, 3), np.float32))[0].tolist() == [-1, -1]
+    m = v.AddMesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    v.Display(m)
+    v.Update()
+    b = _parse_blob(v.ExportBVH())
+    assert b["hdr"]["n_nodes"] == 2 and b["info"][0][0] == 1 and b["info"][1][0] == -1   # top leaf + bottom leaf
+    # vertex normals synthesised from the face when the caller gives none
+    assert np.allclose(b["nrm"], [[0, 0, 1]] * 3)
+    v.Remove()
+
+
+def test_material_semantics_follow_cadrays():
+    # MaterialEditor.cxx:294-329: clamp to [0,1], Le and absorption coefficient >= 0, normalise Kd+Ks+Kt
+    b = Graphic3d_BSDF(Kd=[1.0, 0.8, 0.2], Ks=[0.3, 0.3, 0.3, 0.1], Le=[-1, 2, 3], Absorption=[2, -1, 0.5, -4]).Normalize()
+    assert max(b.Kd[k] + b.Ks[k] + b.Kt[k] for k in range(3)) == pytest.approx(1.0)
+    assert b.Kd[0] == pytest.approx(1.0 / 1.3) and b.Ks[3] == 0.1
+    assert b.Le == [0.0, 2.0, 3.0] and b.Absorption == [1.0, 0.0, 0.5, 0.0]
+    # Graphic3d_Fresnel::Serialize (MaterialEditor.cxx:209-255; ImportExport.cxx:204-227)
+    assert Graphic3d_Fresnel.CreateSchlick(0.58, 0.42, 0.2).Serialize()[:3] == pytest.approx((0.58, 0.42, 0.2))
+    assert Graphic3d_Fresnel.CreateConstant(0.7).Serialize()[0] == -1 and Graphic3d_Fresnel.CreateConstant(0.7).Serialize()[2] == pytest.approx(0.7)
+    assert Graphic3d_Fresnel.CreateConductor(0.8, 5.8).Serialize()[:3] == pytest.approx((-2, 0.8, 5.8))
+    assert Graphic3d_Fresnel.CreateDielectric(1.5).Serialize()[:2] == pytest.approx((-3, 1.5))
+    g = Graphic3d_BSDF.CreateGlass((1, 1, 1), (0.8, 0.8, 1.0), 6.0, 1.5).to_c()
+    assert list(g.Kt)[:3] == [1, 1, 1] and g.FresnelCoat[0] == -3 and g.Absorption[3] == 6.0
+    with pytest.raises(ValueError):
+        Graphic3d_RenderingParams(IsGlobalIlluminationEnabled=False).to_c()
+    with pytest.raises(ValueError):
+        Graphic3d_RenderingParams(AdaptiveScreenSampling=True).to_c()
+
+
+def test_scene_generators_are_seeded_and_sized():
+    a = scenes.assembly(n_parts=30, target_tris=15000, seed=2)
+    b = scenes.assembly(n_parts=30, target_tris=15000, seed=2)
+    c = scenes.assembly(n_parts=30, target_tris=15000, seed=3)
+    assert a.n_triangles() == b.n_triangles() and abs(a.n_triangles() - 15000) <= 0.05 * 15000
+    assert all(np.array_equal(x[1], y[1]) for x, y in zip(a.instances, b.instances))
+    assert not all(np.array_equal(x[1], y[1]) for x, y in zip(a.instances[:-1], c.instances[:-1]))
+    inst = scenes.instanced(n_inst=8, n_meshes=2, nu=80, nv=65)
+    assert inst.meshes[0][2].shape[0] == 10240                      # config C5 mesh size
+    cb = scenes.cornell_box()
+    assert len(cb.instances) == 9 and cb.lights[0].is_point == 1 and cb.lights[0].smoothness == pytest.approx(0.06)
+    ms = scenes.materials_scene(sphere_res=(16, 8))
+    assert len(ms.instances) == 144 + 9 and ms.camera.FOVy == 25.0
