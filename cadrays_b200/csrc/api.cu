@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -105,6 +106,10 @@ struct crt_context {
   // read-back staging
   DevBuf<uint8_t> d_ldr;
   DevBuf<float> d_hdr;
+
+  // traversal driver: per-lane-refill persistent kernels (default) or the static form (A/B knob:
+  // environment CRT_TRAVERSAL=static)
+  bool persistent = true;
 
   // metrics
   DevBuf<Counters> d_counters;
@@ -287,6 +292,18 @@ int upload_tables(crt_context* c)
 
 int grid_for(const crt_context* c, int blocks_per_sm) { return c->sm_count * blocks_per_sm; }
 
+// grid of a persistent kernel = the CTAs that are resident at once (SM count x occupancy)
+template <typename K>
+int resident_grid(const crt_context* c, K kernel, int block)
+{
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  return c->sm_count * per_sm;
+}
+
 template <bool COUNT>
 int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
 {
@@ -298,8 +315,13 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   const int depth_max = c->dp.max_depth;
   st.n_active = c->counters.p;
   st.n_shadow = c->counters.p + (depth_max + 1);
+  st.work_extend = st.n_shadow + depth_max;
+  st.work_connect = st.work_extend + depth_max;
   Counters* gc = c->d_counters.p;
-  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (2 * depth_max + 2), c->stream));
+  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (4 * depth_max + 2), c->stream));
+  const bool pers = c->persistent;
+  static const int g_ext = resident_grid(c, k_extend<COUNT, true>, 128);
+  static const int g_con = resident_grid(c, k_connect<COUNT, true>, 128);
   {
     SpanGuard g(c, F_GENERATE);
     k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
@@ -307,7 +329,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   for (int depth = 0; depth < depth_max; ++depth) {
     {
       SpanGuard g(c, F_EXTEND);
-      k_extend<COUNT><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (pers) k_extend<COUNT, true><<<g_ext, 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_extend<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE);
@@ -315,7 +338,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     }
     {
       SpanGuard g(c, F_CONNECT);
-      k_connect<COUNT><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (pers) k_connect<COUNT, true><<<g_con, 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_connect<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
     }
   }
   {
@@ -338,7 +362,7 @@ int render_impl(crt_context* c, uint32_t n_samples)
   if (n_samples == 0) return CRT_OK;
   const uint32_t batch = std::min(auto_batch(c), n_samples);
   if ((rc = ensure_path_state(c, batch))) return rc;
-  CRT_CUDA(c->counters.ensure(2 * 64 + 4));
+  CRT_CUDA(c->counters.ensure(4 * 64 + 8));
   CRT_CUDA(c->seeds.ensure(n_samples));
   c->h_seeds.resize(n_samples);
   for (uint32_t k = 0; k < n_samples; ++k) c->h_seeds[k] = frame_seed(c, c->next_sample + k);
@@ -415,6 +439,7 @@ int crt_create(int device_ordinal, crt_context** out)
   if (!c) return fail(CRT_ERR_OUT_OF_MEMORY, "host allocation failed");
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   crt_params_default(&c->params);
   std::memset(&c->cam, 0, sizeof c->cam);
   c->cam.dir[1] = 1.0f; c->cam.up[2] = 1.0f; c->cam.fovy_deg = 45.0f; c->cam.aspect = 1.0f; c->cam.ortho_scale = 1.0f;
@@ -792,15 +817,24 @@ int crt_trace_device(crt_context* c, const void* org4, const void* dir4, uint32_
   float4* h = static_cast<float4*>(hit4);
   int32_t* hi = static_cast<int32_t*>(inst);
   Counters* gc = c->d_counters.p;
-  const int grid = std::min<int>(grid_for(c, 16), (int)((n + 127u) / 128u));
+  CRT_CUDA(c->counters.ensure(4 * 64 + 8));
+  uint32_t* work = c->counters.p + 4 * 64 + 4;
+  CRT_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t), c->stream));
+  const bool pers = c->persistent;
+  const int sgrid = std::min<int>(grid_for(c, 16), (int)((n + 127u) / 128u));
   SpanGuard g(c, any_hit ? F_CONNECT : F_EXTEND);
-  if (any_hit) {
-    if (c->stats_on) k_trace<true, true><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
-    else k_trace<true, false><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
-  } else {
-    if (c->stats_on) k_trace<false, true><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
-    else k_trace<false, false><<<grid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, gc);
-  }
+#define CRT_LAUNCH_TRACE(ANY, CNT)                                                                                   \
+  do {                                                                                                               \
+    if (pers) {                                                                                                      \
+      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true>, 128), (int)((n + 31u) / 32u));          \
+      k_trace<ANY, CNT, true><<<pg, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                           \
+    } else {                                                                                                         \
+      k_trace<ANY, CNT, false><<<sgrid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                       \
+    }                                                                                                                \
+  } while (0)
+  if (any_hit) { if (c->stats_on) CRT_LAUNCH_TRACE(true, true); else CRT_LAUNCH_TRACE(true, false); }
+  else { if (c->stats_on) CRT_LAUNCH_TRACE(false, true); else CRT_LAUNCH_TRACE(false, false); }
+#undef CRT_LAUNCH_TRACE
   CRT_CUDA(cudaGetLastError());
   return CRT_OK;
 }

@@ -67,6 +67,8 @@ struct PathState {
   float4* sh_c;       // throughput * contribution
   uint32_t* n_active; // [max_depth + 1]
   uint32_t* n_shadow; // [max_depth]
+  uint32_t* work_extend;   // [max_depth] persistent-kernel work counters
+  uint32_t* work_connect;  // [max_depth]
 };
 
 // ------------------------------------------------------------------ traversal
@@ -120,23 +122,44 @@ __device__ __forceinline__ v3 xf_vector(float4 r0, float4 r1, float4 r2, v3 p)
 
 // SceneNearestHit / SceneAnyHit over the 64-byte two-child nodes.
 // One thread per ray, stack of child references in local memory.  References:
-// >= 0 inner node, bit31 set = leaf (bit30 set = instance, else first triangle).
+// >= 0 inner node, bit31 set = leaf (bit30 set = instance, else first triangle),
+// kDone = traversal finished.
+//
+// Control flow is the "while-while" form: an inner loop that only walks inner nodes,
+// then one leaf / instance step, with no `continue` across the two.  The loops are
+// structured so the compiler can place a reconvergence point after the inner loop;
+// a flat loop with `continue` in its branches leaves warps permanently fragmented
+// (measured: 5 of 32 lanes active per instruction, profiles/r01_*).
+constexpr int32_t kDone = -1;
+
+__device__ __forceinline__ int32_t stack_pop(const int32_t* stack, int& sp, Ray& r, v3 org, v3 dir)
+{
+  if (sp == 0) return kDone;
+  int32_t c = stack[--sp];
+  if (c == kSentinel) {          // leaving an instance: back to the world-space ray
+    r.setup(org, dir);
+    if (sp == 0) return kDone;
+    c = stack[--sp];
+  }
+  return c;
+}
+
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, float tmax, Hit& hit, Counters& cnt)
 {
   hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
-  if (S.top_root == kNoRef) return false;
-  if (!(dot3(dir, dir) > 0.0f) || !(dot3(org, org) >= 0.0f)) return false;
+  int32_t cur = S.top_root;
+  if (cur == kNoRef) cur = kDone;
+  if (!(dot3(dir, dir) > 0.0f) || !(dot3(org, org) >= 0.0f)) cur = kDone;
   int32_t stack[kStackSize];
   int sp = 0;
-  int32_t cur = S.top_root;
   int32_t inst = -1;
   Ray r;
   r.setup(org, dir);
   bool found = false;
-  for (;;) {
-    if (cur >= 0) {
-      // ---- inner node: test both children, descend into the nearer one
+  while (cur != kDone) {
+    // ---- inner nodes: test both children, descend into the nearer one, push the farther
+    while (cur >= 0) {
       if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
       const float4* nd = S.nodes + 4 * (size_t)cur;
       const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
@@ -153,15 +176,16 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
       const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
       const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
       const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-      if (h0 && h1) {
-        const bool swap = te1 < te0;
+      if (h0 | h1) {
+        const bool swap = h1 && (!h0 || te1 < te0);   // go to child 1 first
         cur = swap ? r1 : r0;
-        stack[sp++] = swap ? r0 : r1;
-        continue;
+        if (h0 & h1) stack[sp++] = swap ? r0 : r1;
+      } else {
+        cur = stack_pop(stack, sp, r, org, dir);
       }
-      if (h0) { cur = r0; continue; }
-      if (h1) { cur = r1; continue; }
-    } else if ((uint32_t)cur & 0x40000000u) {
+    }
+    if (cur == kDone) break;
+    if ((uint32_t)cur & 0x40000000u) {
       // ---- top-level leaf: enter the instance (ray to object space, not renormalised)
       if (COUNT) { if (ANY) cnt.n_switch_any++; else cnt.n_switch++; }
       inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
@@ -170,35 +194,147 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
       r.setup(xf_point(m0, m1, m2, org), xf_vector(m0, m1, m2, dir));
       stack[sp++] = kSentinel;
       cur = __float_as_int(m3.x);
-      continue;
     } else {
       // ---- bottom-level leaf: triangles until the "last" flag
       if (COUNT) { if (ANY) cnt.n_leaf_any++; else cnt.n_leaf++; }
       uint32_t tri = (uint32_t)cur & 0x3fffffffu;
-      for (;;) {
+      bool more = true;
+      while (more) {
         if (COUNT) { if (ANY) cnt.n_tri_any++; else cnt.n_tri++; }
         const float4* tv = S.tri_verts + 3 * (size_t)tri;
         const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
         float t, u, v;
+        more = __float_as_int(b.w) == 0;
         if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
           hit.t = t; hit.u = u; hit.v = v; hit.tri = (int32_t)tri; hit.inst = inst;
           found = true;
-          if (ANY) return true;
+          if (ANY) more = false;
         }
-        if (__float_as_int(b.w) != 0) break;
         ++tri;
       }
-    }
-    // ---- pop
-    if (sp == 0) break;
-    cur = stack[--sp];
-    if (cur == kSentinel) {
-      r.setup(org, dir);
-      if (sp == 0) break;
-      cur = stack[--sp];
+      cur = (ANY && found) ? kDone : stack_pop(stack, sp, r, org, dir);
     }
   }
   return found;
+}
+
+// Persistent-thread form of the same traversal: every lane owns one ray at a time and
+// takes the next one from a warp-local pool the moment its ray finishes, instead of
+// idling until the slowest ray of the warp is done.  The pool is refilled kChunk rays
+// at a time with one atomicAdd per warp on a per-launch work counter; lanes pick from
+// it with a ballot prefix (no further atomics).  Per outer iteration a lane does:
+// retire/refill -> walk inner nodes until a leaf reference -> one leaf or instance step.
+// Identical arithmetic and visiting order per ray as traverse<>, so results and work
+// counters are unchanged.  Policy supplies load(index) / store(token, hit, found).
+constexpr uint32_t kChunk = 64;
+
+template <bool ANY, bool COUNT, class Policy>
+__device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t n, uint32_t* work, Counters& cnt,
+                                                 const Policy& pol)
+{
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t pool_next = 0, pool_end = 0;   // warp-uniform
+  bool drained = false;                   // warp-uniform: the launch's queue is exhausted
+  int32_t cur = kDone;
+  bool has_ray = false, found = false;
+  uint32_t token = 0;
+  v3 org = V(0, 0, 0), dir = V(0, 0, 1);
+  Ray r;
+  r.setup(org, dir);
+  Hit hit;
+  hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
+  int32_t stack[kStackSize];
+  int sp = 0;
+  int32_t inst = -1;
+  for (;;) {
+    // ---- retire finished rays, hand out new ones
+    if (cur == kDone && has_ray) { pol.store(token, hit, found); has_ray = false; }
+    const bool need = cur == kDone;
+    const unsigned m = __ballot_sync(FULL, need);
+    if (m) {
+      if (pool_next == pool_end && !drained) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, kChunk);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) drained = true;
+        else { pool_next = base; pool_end = min(base + kChunk, n); }
+      }
+      const uint32_t avail = pool_end - pool_next;
+      const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+      if (need && rank < avail) {
+        float tmax;
+        token = pol.load(pool_next + rank, org, dir, tmax);
+        hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
+        found = false; sp = 0; inst = -1;
+        cur = S.top_root;
+        if (cur == kNoRef) cur = kDone;
+        if (!(dot3(dir, dir) > 0.0f) || !(dot3(org, org) >= 0.0f)) cur = kDone;
+        r.setup(org, dir);
+        has_ray = true;
+        if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
+      }
+      pool_next += min(avail, (uint32_t)__popc(m));
+    }
+    if (drained && __all_sync(FULL, !has_ray)) break;
+
+    // ---- inner nodes
+    while (cur >= 0) {
+      if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
+      const float4* nd = S.nodes + 4 * (size_t)cur;
+      const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+      const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
+      const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
+      const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
+      const float c1x0 = fmaf(n1.x, r.inv.x, r.oinv.x), c1x1 = fmaf(n1.y, r.inv.x, r.oinv.x);
+      const float c1y0 = fmaf(n1.z, r.inv.y, r.oinv.y), c1y1 = fmaf(n1.w, r.inv.y, r.oinv.y);
+      const float c1z0 = fmaf(n2.z, r.inv.z, r.oinv.z), c1z1 = fmaf(n2.w, r.inv.z, r.oinv.z);
+      const float te0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fminf(c0z0, c0z1));
+      const float tx0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fmaxf(c0z0, c0z1));
+      const float te1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fminf(c1z0, c1z1));
+      const float tx1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fmaxf(c1z0, c1z1));
+      const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
+      const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
+      const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+      if (h0 | h1) {
+        const bool swap = h1 && (!h0 || te1 < te0);
+        cur = swap ? r1 : r0;
+        if (h0 & h1) stack[sp++] = swap ? r0 : r1;
+      } else {
+        cur = stack_pop(stack, sp, r, org, dir);
+      }
+    }
+    // ---- one leaf / instance step
+    if (cur != kDone) {
+      if ((uint32_t)cur & 0x40000000u) {
+        if (COUNT) { if (ANY) cnt.n_switch_any++; else cnt.n_switch++; }
+        inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
+        const float4* ir = S.inst + 4 * (size_t)inst;
+        const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+        r.setup(xf_point(m0, m1, m2, org), xf_vector(m0, m1, m2, dir));
+        stack[sp++] = kSentinel;
+        cur = __float_as_int(m3.x);
+      } else {
+        if (COUNT) { if (ANY) cnt.n_leaf_any++; else cnt.n_leaf++; }
+        uint32_t tri = (uint32_t)cur & 0x3fffffffu;
+        bool more = true;
+        while (more) {
+          if (COUNT) { if (ANY) cnt.n_tri_any++; else cnt.n_tri++; }
+          const float4* tv = S.tri_verts + 3 * (size_t)tri;
+          const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+          float t, u, v;
+          more = __float_as_int(b.w) == 0;
+          if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
+            hit.t = t; hit.u = u; hit.v = v; hit.tri = (int32_t)tri; hit.inst = inst;
+            found = true;
+            if (ANY) more = false;
+          }
+          ++tri;
+        }
+        cur = (ANY && found) ? kDone : stack_pop(stack, sp, r, org, dir);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ BSDF
@@ -605,22 +741,45 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
   }
 }
 
-// SceneNearestHit for every active path.
-template <bool COUNT>
+struct ExtendPolicy {
+  PathState st;
+  const uint32_t* __restrict__ q;
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  {
+    const uint32_t slot = q[i];
+    const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = CRT_MAXFLOAT;
+    return slot;
+  }
+  __device__ __forceinline__ void store(uint32_t slot, const Hit& hit, bool) const
+  {
+    st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+    st.hit_inst[slot] = hit.inst;
+  }
+};
+
+// SceneNearestHit for every active path.  PERSISTENT selects the per-lane-refill driver
+// (grid = resident CTAs) or the static one-ray-per-loop-iteration form (kept for A/B).
+template <bool COUNT, bool PERSISTENT>
 __global__ void __launch_bounds__(128)
 k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_active[depth];
   const uint32_t* __restrict__ q = st.queue[depth & 1];
   Counters cnt = {};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t slot = q[i];
-    const float4 o = st.ray_o[slot], d = st.ray_d[slot];
-    Hit hit;
-    traverse<false, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), CRT_MAXFLOAT, hit, cnt);
-    if (COUNT) cnt.rays_nearest++;
-    st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
-    st.hit_inst[slot] = hit.inst;
+  if (PERSISTENT) {
+    ExtendPolicy pol{ st, q };
+    trace_persistent<false, COUNT>(S, n, st.work_extend + depth, cnt, pol);
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const uint32_t slot = q[i];
+      const float4 o = st.ray_o[slot], d = st.ray_d[slot];
+      Hit hit;
+      traverse<false, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), CRT_MAXFLOAT, hit, cnt);
+      if (COUNT) cnt.rays_nearest++;
+      st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+      st.hit_inst[slot] = hit.inst;
+    }
   }
   if (COUNT) flush_counters(gcnt, cnt);
 }
@@ -782,24 +941,48 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
   if (COUNT) flush_counters(gcnt, cnt);
 }
 
+struct ConnectPolicy {
+  PathState st;
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  {
+    const float4 ro = st.sh_o[i], rd = st.sh_d[i];
+    o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = ro.w;
+    return i;
+  }
+  __device__ __forceinline__ void store(uint32_t i, const Hit&, bool occluded) const
+  {
+    if (occluded) return;
+    const uint32_t slot = __float_as_uint(st.sh_d[i].w);
+    const float4 c = st.sh_c[i];
+    float4 r = st.rad[slot];
+    r.x += c.x; r.y += c.y; r.z += c.z;
+    st.rad[slot] = r;
+  }
+};
+
 // SceneAnyHit for the shadow rays of this bounce; visible => add the contribution.
-template <bool COUNT>
+template <bool COUNT, bool PERSISTENT>
 __global__ void __launch_bounds__(128)
 k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_shadow[depth];
   Counters cnt = {};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 o = st.sh_o[i], d = st.sh_d[i];
-    Hit hit;
-    const bool occluded = traverse<true, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, hit, cnt);
-    if (COUNT) cnt.rays_any++;
-    if (!occluded) {
-      const uint32_t slot = __float_as_uint(d.w);
-      const float4 c = st.sh_c[i];
-      float4 r = st.rad[slot];
-      r.x += c.x; r.y += c.y; r.z += c.z;
-      st.rad[slot] = r;
+  if (PERSISTENT) {
+    ConnectPolicy pol{ st };
+    trace_persistent<true, COUNT>(S, n, st.work_connect + depth, cnt, pol);
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const float4 o = st.sh_o[i], d = st.sh_d[i];
+      Hit hit;
+      const bool occluded = traverse<true, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, hit, cnt);
+      if (COUNT) cnt.rays_any++;
+      if (!occluded) {
+        const uint32_t slot = __float_as_uint(d.w);
+        const float4 c = st.sh_c[i];
+        float4 r = st.rad[slot];
+        r.x += c.x; r.y += c.y; r.z += c.z;
+        st.rad[slot] = r;
+      }
     }
   }
   if (COUNT) flush_counters(gcnt, cnt);
@@ -859,22 +1042,47 @@ k_display(const float4* __restrict__ accum, uint32_t n_pixels, float exposure_sc
   }
 }
 
-// Batch SceneNearestHit / SceneAnyHit on caller rays (parity hook crt_trace).
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128)
-k_trace(DeviceScene S, const float4* __restrict__ org, const float4* __restrict__ dir, uint32_t n,
-        float4* __restrict__ hit4, int32_t* __restrict__ hit_inst, Counters* gcnt)
-{
-  Counters cnt = {};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 o = org[i], d = dir[i];
-    Hit hit;
-    const bool f = traverse<ANY, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), d.w, hit, cnt);
-    if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
+template <bool ANY>
+struct TracePolicy {
+  const float4* __restrict__ org;
+  const float4* __restrict__ dir;
+  float4* __restrict__ hit4;
+  int32_t* __restrict__ hit_inst;
+  const float4* __restrict__ tri_verts;
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  {
+    const float4 ro = org[i], rd = dir[i];
+    o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = rd.w;
+    return i;
+  }
+  __device__ __forceinline__ void store(uint32_t i, const Hit& hit, bool f) const
+  {
     int32_t prim = -1;
-    if (f) prim = ANY ? 0 : __float_as_int(__ldg(S.tri_verts + 3 * (size_t)hit.tri).w);
+    if (f) prim = ANY ? 0 : __float_as_int(__ldg(tri_verts + 3 * (size_t)hit.tri).w);
     hit4[i] = make_float4(hit.t, hit.u, hit.v, __int_as_float(prim));
     if (hit_inst) hit_inst[i] = hit.inst;
+  }
+};
+
+// Batch SceneNearestHit / SceneAnyHit on caller rays (parity hook crt_trace).
+template <bool ANY, bool COUNT, bool PERSISTENT>
+__global__ void __launch_bounds__(128)
+k_trace(DeviceScene S, const float4* __restrict__ org, const float4* __restrict__ dir, uint32_t n,
+        float4* __restrict__ hit4, int32_t* __restrict__ hit_inst, uint32_t* work, Counters* gcnt)
+{
+  Counters cnt = {};
+  TracePolicy<ANY> pol{ org, dir, hit4, hit_inst, S.tri_verts };
+  if (PERSISTENT) {
+    trace_persistent<ANY, COUNT>(S, n, work, cnt, pol);
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      v3 o, d; float tmax;
+      pol.load(i, o, d, tmax);
+      Hit hit;
+      const bool f = traverse<ANY, COUNT>(S, o, d, tmax, hit, cnt);
+      if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
+      pol.store(i, hit, f);
+    }
   }
   if (COUNT) flush_counters(gcnt, cnt);
 }
