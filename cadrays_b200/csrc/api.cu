@@ -110,6 +110,7 @@ struct crt_context {
   // traversal driver: per-lane-refill persistent kernels (default) or the static form (A/B knob:
   // environment CRT_TRAVERSAL=static)
   bool persistent = true;
+  bool fuse_traversal = true;   // connect(d) + extend(d+1) in one launch (CRT_FUSE=0 disables)
 
   // metrics
   DevBuf<Counters> d_counters;
@@ -229,7 +230,7 @@ uint32_t auto_batch(const crt_context* c)
   if (c->params.samples_per_batch > 0) return (uint32_t)c->params.samples_per_batch;
   const uint64_t px = (uint64_t)c->width * c->height;
   if (!px) return 1;
-  uint64_t b = (8ull << 20) / px;   // about 8 M paths in flight
+  uint64_t b = (16ull << 20) / px;  // about 16 M paths in flight (2.6 GB of path state)
   return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b, 64));
 }
 
@@ -320,23 +321,27 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   Counters* gc = c->d_counters.p;
   CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (4 * depth_max + 2), c->stream));
   const bool pers = c->persistent;
+  const bool fuse = pers && c->fuse_traversal;
   static const int g_ext = resident_grid(c, k_extend<COUNT, true>, 128);
   static const int g_con = resident_grid(c, k_connect<COUNT, true>, 128);
+  static const int g_dual = resident_grid(c, k_trace_dual<COUNT>, 128);
   {
     SpanGuard g(c, F_GENERATE);
     k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
   }
   for (int depth = 0; depth < depth_max; ++depth) {
+    // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND);
-      if (pers) k_extend<COUNT, true><<<g_ext, 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (fuse && depth > 0) k_trace_dual<COUNT><<<g_dual, 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      else if (pers) k_extend<COUNT, true><<<g_ext, 128, 0, c->stream>>>(c->ds, st, depth, gc);
       else k_extend<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE);
       k_shade<COUNT><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
     }
-    {
+    if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT);
       if (pers) k_connect<COUNT, true><<<g_con, 128, 0, c->stream>>>(c->ds, st, depth, gc);
       else k_connect<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
@@ -440,6 +445,8 @@ int crt_create(int device_ordinal, crt_context** out)
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
+  if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
+
   crt_params_default(&c->params);
   std::memset(&c->cam, 0, sizeof c->cam);
   c->cam.dir[1] = 1.0f; c->cam.up[2] = 1.0f; c->cam.fovy_deg = 45.0f; c->cam.aspect = 1.0f; c->cam.ortho_scale = 1.0f;

@@ -228,7 +228,9 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 // counters are unchanged.  Policy supplies load(index) / store(token, hit, found).
 constexpr uint32_t kChunk = 64;
 
-template <bool ANY, bool COUNT, class Policy>
+// MODE 0: closest hit for every ray, 1: any hit for every ray, 2: per ray (Policy::load says which;
+// used by the fused "connect(d) + extend(d+1)" launch).
+template <int MODE, bool COUNT, class Policy>
 __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t n, uint32_t* work, Counters& cnt,
                                                  const Policy& pol)
 {
@@ -237,7 +239,7 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   uint32_t pool_next = 0, pool_end = 0;   // warp-uniform
   bool drained = false;                   // warp-uniform: the launch's queue is exhausted
   int32_t cur = kDone;
-  bool has_ray = false, found = false;
+  bool has_ray = false, found = false, any_ray = (MODE == 1);
   uint32_t token = 0;
   v3 org = V(0, 0, 0), dir = V(0, 0, 1);
   Ray r;
@@ -249,7 +251,7 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   int32_t inst = -1;
   for (;;) {
     // ---- retire finished rays, hand out new ones
-    if (cur == kDone && has_ray) { pol.store(token, hit, found); has_ray = false; }
+    if (cur == kDone && has_ray) { pol.store(token, hit, found, any_ray); has_ray = false; }
     const bool need = cur == kDone;
     const unsigned m = __ballot_sync(FULL, need);
     if (m) {
@@ -264,7 +266,9 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
       const uint32_t rank = __popc(m & ((1u << lane) - 1u));
       if (need && rank < avail) {
         float tmax;
-        token = pol.load(pool_next + rank, org, dir, tmax);
+        bool a = (MODE == 1);
+        token = pol.load(pool_next + rank, org, dir, tmax, a);
+        if (MODE == 2) any_ray = a;
         hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
         found = false; sp = 0; inst = -1;
         cur = S.top_root;
@@ -272,42 +276,45 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         if (!(dot3(dir, dir) > 0.0f) || !(dot3(org, org) >= 0.0f)) cur = kDone;
         r.setup(org, dir);
         has_ray = true;
-        if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
+        if (COUNT) { if (any_ray) cnt.rays_any++; else cnt.rays_nearest++; }
       }
       pool_next += min(avail, (uint32_t)__popc(m));
     }
     if (drained && __all_sync(FULL, !has_ray)) break;
 
-    // ---- inner nodes
+    // ---- inner nodes.  (A variant that left this loop once fewer than N lanes were still walking
+    // inner nodes was measured: the two extra votes per iteration cost more than the regained lanes.)
     while (cur >= 0) {
-      if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
-      const float4* nd = S.nodes + 4 * (size_t)cur;
-      const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
-      const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
-      const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
-      const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
-      const float c1x0 = fmaf(n1.x, r.inv.x, r.oinv.x), c1x1 = fmaf(n1.y, r.inv.x, r.oinv.x);
-      const float c1y0 = fmaf(n1.z, r.inv.y, r.oinv.y), c1y1 = fmaf(n1.w, r.inv.y, r.oinv.y);
-      const float c1z0 = fmaf(n2.z, r.inv.z, r.oinv.z), c1z1 = fmaf(n2.w, r.inv.z, r.oinv.z);
-      const float te0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fminf(c0z0, c0z1));
-      const float tx0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fmaxf(c0z0, c0z1));
-      const float te1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fminf(c1z0, c1z1));
-      const float tx1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fmaxf(c1z0, c1z1));
-      const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
-      const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
-      const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-      if (h0 | h1) {
-        const bool swap = h1 && (!h0 || te1 < te0);
-        cur = swap ? r1 : r0;
-        if (h0 & h1) stack[sp++] = swap ? r0 : r1;
-      } else {
-        cur = stack_pop(stack, sp, r, org, dir);
+      {
+        if (COUNT) { if (any_ray) cnt.n_inner_any++; else cnt.n_inner++; }
+        const float4* nd = S.nodes + 4 * (size_t)cur;
+        const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+        const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
+        const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
+        const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
+        const float c1x0 = fmaf(n1.x, r.inv.x, r.oinv.x), c1x1 = fmaf(n1.y, r.inv.x, r.oinv.x);
+        const float c1y0 = fmaf(n1.z, r.inv.y, r.oinv.y), c1y1 = fmaf(n1.w, r.inv.y, r.oinv.y);
+        const float c1z0 = fmaf(n2.z, r.inv.z, r.oinv.z), c1z1 = fmaf(n2.w, r.inv.z, r.oinv.z);
+        const float te0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fminf(c0z0, c0z1));
+        const float tx0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fmaxf(c0z0, c0z1));
+        const float te1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fminf(c1z0, c1z1));
+        const float tx1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fmaxf(c1z0, c1z1));
+        const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
+        const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
+        const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+        if (h0 | h1) {
+          const bool swap = h1 && (!h0 || te1 < te0);
+          cur = swap ? r1 : r0;
+          if (h0 & h1) stack[sp++] = swap ? r0 : r1;
+        } else {
+          cur = stack_pop(stack, sp, r, org, dir);
+        }
       }
     }
     // ---- one leaf / instance step
-    if (cur != kDone) {
+    if (cur < 0 && cur != kDone) {
       if ((uint32_t)cur & 0x40000000u) {
-        if (COUNT) { if (ANY) cnt.n_switch_any++; else cnt.n_switch++; }
+        if (COUNT) { if (any_ray) cnt.n_switch_any++; else cnt.n_switch++; }
         inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
         const float4* ir = S.inst + 4 * (size_t)inst;
         const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
@@ -315,11 +322,11 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         stack[sp++] = kSentinel;
         cur = __float_as_int(m3.x);
       } else {
-        if (COUNT) { if (ANY) cnt.n_leaf_any++; else cnt.n_leaf++; }
+        if (COUNT) { if (any_ray) cnt.n_leaf_any++; else cnt.n_leaf++; }
         uint32_t tri = (uint32_t)cur & 0x3fffffffu;
         bool more = true;
         while (more) {
-          if (COUNT) { if (ANY) cnt.n_tri_any++; else cnt.n_tri++; }
+          if (COUNT) { if (any_ray) cnt.n_tri_any++; else cnt.n_tri++; }
           const float4* tv = S.tri_verts + 3 * (size_t)tri;
           const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
           float t, u, v;
@@ -327,11 +334,11 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
           if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
             hit.t = t; hit.u = u; hit.v = v; hit.tri = (int32_t)tri; hit.inst = inst;
             found = true;
-            if (ANY) more = false;
+            if (any_ray) more = false;
           }
           ++tri;
         }
-        cur = (ANY && found) ? kDone : stack_pop(stack, sp, r, org, dir);
+        cur = (any_ray && found) ? kDone : stack_pop(stack, sp, r, org, dir);
       }
     }
   }
@@ -744,14 +751,14 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
 struct ExtendPolicy {
   PathState st;
   const uint32_t* __restrict__ q;
-  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool&) const
   {
     const uint32_t slot = q[i];
     const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
     o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = CRT_MAXFLOAT;
     return slot;
   }
-  __device__ __forceinline__ void store(uint32_t slot, const Hit& hit, bool) const
+  __device__ __forceinline__ void store(uint32_t slot, const Hit& hit, bool, bool) const
   {
     st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
     st.hit_inst[slot] = hit.inst;
@@ -769,7 +776,7 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
   Counters cnt = {};
   if (PERSISTENT) {
     ExtendPolicy pol{ st, q };
-    trace_persistent<false, COUNT>(S, n, st.work_extend + depth, cnt, pol);
+    trace_persistent<0, COUNT>(S, n, st.work_extend + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const uint32_t slot = q[i];
@@ -943,13 +950,13 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
 
 struct ConnectPolicy {
   PathState st;
-  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool&) const
   {
     const float4 ro = st.sh_o[i], rd = st.sh_d[i];
     o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = ro.w;
     return i;
   }
-  __device__ __forceinline__ void store(uint32_t i, const Hit&, bool occluded) const
+  __device__ __forceinline__ void store(uint32_t i, const Hit&, bool occluded, bool) const
   {
     if (occluded) return;
     const uint32_t slot = __float_as_uint(st.sh_d[i].w);
@@ -969,7 +976,7 @@ k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
   Counters cnt = {};
   if (PERSISTENT) {
     ConnectPolicy pol{ st };
-    trace_persistent<true, COUNT>(S, n, st.work_connect + depth, cnt, pol);
+    trace_persistent<1, COUNT>(S, n, st.work_connect + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const float4 o = st.sh_o[i], d = st.sh_d[i];
@@ -985,6 +992,38 @@ k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
       }
     }
   }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// Fused launch: the shadow rays of bounce depth-1 (any hit) and the continuation rays of bounce
+// depth (closest hit) are independent, so one persistent launch walks both queues; this halves the
+// number of latency-bound launch tails per bounce.  Index space: [0, n_ext) continuation rays,
+// [n_ext, n_ext + n_sh) shadow rays.
+struct DualPolicy {
+  ExtendPolicy ext;
+  ConnectPolicy con;
+  uint32_t n_ext;
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool& any) const
+  {
+    any = i >= n_ext;
+    return any ? con.load(i - n_ext, o, d, tmax, any) : ext.load(i, o, d, tmax, any);
+  }
+  __device__ __forceinline__ void store(uint32_t token, const Hit& hit, bool found, bool any) const
+  {
+    if (any) con.store(token, hit, found, true);
+    else ext.store(token, hit, found, false);
+  }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
+{
+  const uint32_t n_ext = st.n_active[depth];
+  const uint32_t n_sh = st.n_shadow[depth - 1];
+  Counters cnt = {};
+  DualPolicy pol{ ExtendPolicy{ st, st.queue[depth & 1] }, ConnectPolicy{ st }, n_ext };
+  trace_persistent<2, COUNT>(S, n_ext + n_sh, st.work_extend + depth, cnt, pol);
   if (COUNT) flush_counters(gcnt, cnt);
 }
 
@@ -1049,13 +1088,13 @@ struct TracePolicy {
   float4* __restrict__ hit4;
   int32_t* __restrict__ hit_inst;
   const float4* __restrict__ tri_verts;
-  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax) const
+  __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool&) const
   {
     const float4 ro = org[i], rd = dir[i];
     o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = rd.w;
     return i;
   }
-  __device__ __forceinline__ void store(uint32_t i, const Hit& hit, bool f) const
+  __device__ __forceinline__ void store(uint32_t i, const Hit& hit, bool f, bool = false) const
   {
     int32_t prim = -1;
     if (f) prim = ANY ? 0 : __float_as_int(__ldg(tri_verts + 3 * (size_t)hit.tri).w);
@@ -1073,11 +1112,11 @@ k_trace(DeviceScene S, const float4* __restrict__ org, const float4* __restrict_
   Counters cnt = {};
   TracePolicy<ANY> pol{ org, dir, hit4, hit_inst, S.tri_verts };
   if (PERSISTENT) {
-    trace_persistent<ANY, COUNT>(S, n, work, cnt, pol);
+    trace_persistent<ANY ? 1 : 0, COUNT>(S, n, work, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      v3 o, d; float tmax;
-      pol.load(i, o, d, tmax);
+      v3 o, d; float tmax; bool unused = false;
+      pol.load(i, o, d, tmax, unused);
       Hit hit;
       const bool f = traverse<ANY, COUNT>(S, o, d, tmax, hit, cnt);
       if (COUNT) { if (ANY) cnt.rays_any++; else cnt.rays_nearest++; }
