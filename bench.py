@@ -203,6 +203,7 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcadrays_b200 has no CPU fallback")
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner out of the one-JSON-line stdout
     rank, local, world = D.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world

@@ -1,0 +1,872 @@
+"""TCL-subset scene loader: runs the path-tracing scripts CADRays ships
+(data/scripts/CornellBox.tcl, data/scripts/Materials.tcl) and the model.tcl files its exporter
+writes (src/ImportExport/ImportExport.cxx:155-231,444-606) without OCCT, Tcl or DRAW.
+
+It is a small Tcl evaluator (set / expr / for / if / incr / eval / lrepeat / puts, $var and [cmd]
+substitution, braces and quotes) plus the DRAW / ViewerTest commands those scripts use:
+
+  shapes   box psphere pcylinder compound explode ttranslate trotate tcopy
+  viewer   vclear vdisplay verase vremove vlocation vsetmaterial vbsdf vlight rtlight vcamera vviewparams
+           vfront vback vtop vbottom vleft vright vaxo vfit vrenderparams vtextureenv vsetdispmode
+           vinit vfps vdump(ignored)
+
+Everything produces a cadrays_b200.scenes.SceneDesc; rendering stays in libcadrays_b200.so.
+Default BSDFs of OCCT's named materials (`vsetmaterial <obj> glass`) live in the absent
+Graphic3d_MaterialAspect.cxx; NAMED_MATERIALS below is a re-derivation (parity unpinned).
+"""
+from __future__ import annotations
+
+import ast
+import math
+import operator
+import os
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import scenes
+from .view import (Graphic3d_BSDF, Graphic3d_Camera, Graphic3d_Fresnel, Graphic3d_RenderingParams,
+                   Graphic3d_ToneMappingMethod_Filmic, make_light)
+
+
+class TclError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------ named materials (re-derived)
+
+def _metal(f0, rough):
+    return lambda: Graphic3d_BSDF(Ks=[0.985, 0.985, 0.985, rough], FresnelBase=Graphic3d_Fresnel.CreateSchlick(*f0))
+
+
+def _diffuse(kd):
+    return lambda: Graphic3d_BSDF(Kd=list(kd))
+
+
+def _plastic(kd, rough=0.1):
+    return lambda: Graphic3d_BSDF(Kd=list(kd), Ks=[0.04, 0.04, 0.04, rough], FresnelBase=Graphic3d_Fresnel.CreateConstant(1.0))
+
+
+NAMED_MATERIALS: Dict[str, Callable[[], Graphic3d_BSDF]] = {
+    "brass": _metal((0.58, 0.42, 0.20), 0.045),            # Schlick colour as used with Brass in Materials.tcl:49
+    "bronze": _metal((0.65, 0.35, 0.15), 0.045),
+    "copper": _metal((0.955, 0.638, 0.538), 0.045),
+    "gold": _metal((1.0, 0.782, 0.344), 0.045),
+    "pewter": _metal((0.55, 0.57, 0.60), 0.2),
+    "silver": _metal((0.972, 0.960, 0.915), 0.045),
+    "steel": _metal((0.56, 0.57, 0.58), 0.1),
+    "chrome": _metal((0.549, 0.556, 0.554), 0.02),
+    "aluminium": _metal((0.913183, 0.921494, 0.924524), 0.026),   # Materials.tcl:159-171
+    "aluminum": _metal((0.913183, 0.921494, 0.924524), 0.026),
+    "plaster": _diffuse((0.482353, 0.482353, 0.482353)),
+    "plastic": _plastic((0.2, 0.2, 0.2)),
+    "shiny_plastic": _plastic((0.2, 0.2, 0.2), 0.02),
+    "satin": _plastic((0.3, 0.3, 0.3), 0.3),
+    "stone": _diffuse((0.5, 0.45, 0.4)),
+    "charcoal": _diffuse((0.05, 0.05, 0.05)),
+    "obsidian": _plastic((0.05, 0.05, 0.07), 0.02),
+    "jade": _plastic((0.3, 0.6, 0.4), 0.1),
+    "neon_gnc": lambda: Graphic3d_BSDF(Kd=[0.1, 0.1, 0.1], Le=[0.0, 1.0, 0.46]),
+    "neon_phc": lambda: Graphic3d_BSDF(Kd=[0.1, 0.1, 0.1], Le=[1.0, 1.0, 1.0]),
+    "glass": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (1, 1, 1), 0.0, 1.5),
+    "water": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (0.8, 0.9, 1.0), 0.1, 1.33),
+    "diamond": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (1, 1, 1), 0.0, 2.42),
+    "default": _plastic((0.6, 0.6, 0.6)),
+}
+
+
+# ------------------------------------------------------------------ a small Tcl evaluator
+
+_BIN = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: None, ast.Mod: operator.mod,
+        ast.Pow: operator.pow, ast.BitAnd: operator.and_, ast.BitOr: operator.or_, ast.BitXor: operator.xor,
+        ast.LShift: operator.lshift, ast.RShift: operator.rshift}
+_CMP = {ast.Eq: operator.eq, ast.NotEq: operator.ne, ast.Lt: operator.lt, ast.LtE: operator.le, ast.Gt: operator.gt, ast.GtE: operator.ge}
+_FUN = {"sin": math.sin, "cos": math.cos, "tan": math.tan, "sqrt": math.sqrt, "abs": abs, "int": int, "double": float,
+        "round": round, "floor": math.floor, "ceil": math.ceil, "pow": math.pow, "atan": math.atan, "atan2": math.atan2,
+        "asin": math.asin, "acos": math.acos, "exp": math.exp, "log": math.log, "min": min, "max": max, "fmod": math.fmod}
+
+
+def tcl_expr(text: str):
+    """Tcl `expr` for the arithmetic the scripts use (C operators, integer division, math functions)."""
+    src = text.replace("&&", " and ").replace("||", " or ").replace("!", " not ").replace(" not =", "!=")
+    tree = ast.parse(src.strip(), mode="eval")
+
+    def ev(n):
+        if isinstance(n, ast.Expression):
+            return ev(n.body)
+        if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)):
+            return n.value
+        if isinstance(n, ast.BinOp):
+            a, b = ev(n.left), ev(n.right)
+            if isinstance(n.op, ast.Div):
+                if isinstance(a, int) and isinstance(b, int):
+                    return a // b          # Tcl integer division
+                return a / b
+            return _BIN[type(n.op)](a, b)
+        if isinstance(n, ast.UnaryOp):
+            v = ev(n.operand)
+            if isinstance(n.op, ast.USub):
+                return -v
+            if isinstance(n.op, ast.UAdd):
+                return +v
+            if isinstance(n.op, ast.Not):
+                return int(not v)
+        if isinstance(n, ast.BoolOp):
+            vals = [ev(v) for v in n.values]
+            return int(all(vals)) if isinstance(n.op, ast.And) else int(any(vals))
+        if isinstance(n, ast.Compare) and len(n.ops) == 1:
+            return int(_CMP[type(n.ops[0])](ev(n.left), ev(n.comparators[0])))
+        if isinstance(n, ast.IfExp):
+            return ev(n.body) if ev(n.test) else ev(n.orelse)
+        if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id in _FUN:
+            return _FUN[n.func.id](*[ev(a) for a in n.args])
+        raise TclError(f"expr: unsupported expression '{text}'")
+    return ev(tree)
+
+
+def _fmt(v) -> str:
+    if isinstance(v, bool):
+        return "1" if v else "0"
+    if isinstance(v, float):
+        return repr(v) if not v.is_integer() or abs(v) > 1e15 else f"{v:.1f}"
+    return str(v)
+
+
+class Interp:
+    """Draw_Interpretor stand-in: command table + variables."""
+
+    def __init__(self):
+        self.vars: Dict[str, str] = {}
+        self.cmds: Dict[str, Callable[[List[str]], Optional[str]]] = {}
+        self.unknown: List[str] = []
+        self.strict = False
+        self.output: List[str] = []
+        for name in ("set", "expr", "for", "if", "incr", "eval", "lrepeat", "puts", "list", "llength", "lindex", "foreach",
+                     "while", "catch", "unset", "append", "string"):
+            self.cmds[name] = getattr(self, "_c_" + name)
+
+    # -- parsing
+    def eval(self, script: str) -> str:
+        result = ""
+        for words in self._commands(script):
+            if not words:
+                continue
+            result = self._dispatch(words)
+        return result
+
+    def _dispatch(self, words: List[str]) -> str:
+        name = words[0]
+        fn = self.cmds.get(name)
+        if fn is None:
+            if self.strict:
+                raise TclError(f'invalid command name "{name}"')
+            self.unknown.append(name)
+            return ""
+        r = fn(words[1:])
+        return "" if r is None else str(r)
+
+    def _commands(self, script: str):
+        i, n = 0, len(script)
+        while i < n:
+            # skip whitespace / separators
+            while i < n and script[i] in " \t\r\n;":
+                i += 1
+            if i >= n:
+                break
+            if script[i] == "#":
+                while i < n and script[i] != "\n":
+                    if script[i] == "\\" and i + 1 < n:
+                        i += 1
+                    i += 1
+                continue
+            words: List[str] = []
+            while i < n and script[i] not in "\n;":
+                while i < n and script[i] in " \t\r":
+                    i += 1
+                if i >= n or script[i] in "\n;":
+                    break
+                if script[i] == "\\" and i + 1 < n and script[i + 1] == "\n":
+                    i += 2
+                    continue
+                w, i = self._word(script, i)
+                words.append(w)
+            yield words
+
+    def _word(self, s: str, i: int):
+        n = len(s)
+        if s[i] == "{":
+            depth, j = 1, i + 1
+            while j < n and depth:
+                if s[j] == "\\":
+                    j += 1
+                elif s[j] == "{":
+                    depth += 1
+                elif s[j] == "}":
+                    depth -= 1
+                j += 1
+            if depth:
+                raise TclError("missing close-brace")
+            return s[i + 1:j - 1], j
+        out = []
+        quoted = s[i] == '"'
+        if quoted:
+            i += 1
+        while i < n:
+            c = s[i]
+            if quoted and c == '"':
+                i += 1
+                break
+            if not quoted and c in " \t\r\n;":
+                break
+            if c == "\\" and i + 1 < n:
+                nxt = s[i + 1]
+                out.append({"n": "\n", "t": "\t", "\n": " "}.get(nxt, nxt))
+                i += 2
+            elif c == "$":
+                j = i + 1
+                if j < n and s[j] == "{":
+                    k = s.index("}", j)
+                    name, j = s[j + 1:k], k + 1
+                else:
+                    while j < n and (s[j].isalnum() or s[j] == "_"):
+                        j += 1
+                    name = s[i + 1:j]
+                if not name:
+                    out.append("$")
+                    i += 1
+                    continue
+                if name not in self.vars:
+                    raise TclError(f'can\'t read "{name}": no such variable')
+                out.append(self.vars[name])
+                i = j
+            elif c == "[":
+                depth, j = 1, i + 1
+                while j < n and depth:
+                    if s[j] == "\\":
+                        j += 1
+                    elif s[j] == "[":
+                        depth += 1
+                    elif s[j] == "]":
+                        depth -= 1
+                    j += 1
+                if depth:
+                    raise TclError("missing close-bracket")
+                out.append(self.eval(s[i + 1:j - 1]))
+                i = j
+            else:
+                out.append(c)
+                i += 1
+        return "".join(out), i
+
+    def subst(self, text: str) -> str:
+        """$var and [cmd] substitution inside a braced expression (used by expr / if / for)."""
+        w, _ = self._word('"' + text.replace('"', '\\"') + '"', 0)
+        return w
+
+    # -- core commands
+    def _c_set(self, a):
+        if len(a) == 1:
+            return self.vars[a[0]]
+        self.vars[a[0]] = a[1]
+        return a[1]
+
+    def _c_unset(self, a):
+        for v in a:
+            self.vars.pop(v, None)
+
+    def _c_append(self, a):
+        self.vars[a[0]] = self.vars.get(a[0], "") + "".join(a[1:])
+        return self.vars[a[0]]
+
+    def _c_expr(self, a):
+        return _fmt(tcl_expr(self.subst(" ".join(a))))
+
+    def _cond(self, text):
+        return bool(tcl_expr(self.subst(text)))
+
+    def _c_for(self, a):
+        init, cond, step, body = a
+        self.eval(init)
+        guard = 0
+        while self._cond(cond):
+            self.eval(body)
+            self.eval(step)
+            guard += 1
+            if guard > 10_000_000:
+                raise TclError("for: runaway loop")
+
+    def _c_while(self, a):
+        guard = 0
+        while self._cond(a[0]):
+            self.eval(a[1])
+            guard += 1
+            if guard > 10_000_000:
+                raise TclError("while: runaway loop")
+
+    def _c_foreach(self, a):
+        var, items, body = a
+        for it in self._split_list(items):
+            self.vars[var] = it
+            self.eval(body)
+
+    def _c_if(self, a):
+        i = 0
+        while i < len(a):
+            if a[i] in ("else",):
+                return self.eval(a[i + 1])
+            if a[i] == "elseif":
+                i += 1
+            cond = a[i]
+            body_i = i + 2 if i + 1 < len(a) and a[i + 1] == "then" else i + 1
+            if self._cond(cond):
+                return self.eval(a[body_i])
+            i = body_i + 1
+        return ""
+
+    def _c_incr(self, a):
+        v = int(self.vars.get(a[0], "0")) + (int(a[1]) if len(a) > 1 else 1)
+        self.vars[a[0]] = str(v)
+        return str(v)
+
+    def _c_eval(self, a):
+        return self.eval(" ".join(a))
+
+    def _c_catch(self, a):
+        try:
+            r = self.eval(a[0])
+            if len(a) > 1:
+                self.vars[a[1]] = r
+            return "0"
+        except Exception as e:  # noqa: BLE001
+            if len(a) > 1:
+                self.vars[a[1]] = str(e)
+            return "1"
+
+    @staticmethod
+    def _split_list(text: str) -> List[str]:
+        out, i, n = [], 0, len(text)
+        while i < n:
+            while i < n and text[i].isspace():
+                i += 1
+            if i >= n:
+                break
+            if text[i] == "{":
+                depth, j = 1, i + 1
+                while j < n and depth:
+                    depth += (text[j] == "{") - (text[j] == "}")
+                    j += 1
+                out.append(text[i + 1:j - 1])
+                i = j
+            else:
+                j = i
+                while j < n and not text[j].isspace():
+                    j += 1
+                out.append(text[i:j])
+                i = j
+        return out
+
+    @staticmethod
+    def _join_list(items) -> str:
+        return " ".join("{" + x + "}" if (not x or any(c.isspace() for c in x)) else x for x in items)
+
+    def _c_lrepeat(self, a):
+        return self._join_list(a[1:] * int(a[0]))
+
+    def _c_list(self, a):
+        return self._join_list(a)
+
+    def _c_llength(self, a):
+        return str(len(self._split_list(a[0])))
+
+    def _c_lindex(self, a):
+        return self._split_list(a[0])[int(a[1])]
+
+    def _c_string(self, a):
+        if a[0] == "length":
+            return str(len(a[1]))
+        if a[0] in ("tolower", "toupper"):
+            return a[1].lower() if a[0] == "tolower" else a[1].upper()
+        raise TclError("string: unsupported subcommand " + a[0])
+
+    def _c_puts(self, a):
+        self.output.append(a[-1] if a else "")
+
+
+# ------------------------------------------------------------------ DRAW / ViewerTest subset
+
+class _Shape:
+    """A DRAW shape: tessellated parts with the shape-level transform baked into the vertices."""
+
+    def __init__(self, parts):
+        self.parts = parts          # list of (pos, nrm, idx)
+        self.faces = None           # for `explode <box> FACE`
+
+    def copy(self):
+        s = _Shape([(p.copy(), n.copy(), i.copy()) for p, n, i in self.parts])
+        if self.faces:
+            s.faces = [f.copy() for f in self.faces]
+        return s
+
+    def transform(self, m: np.ndarray):
+        R, t = m[:, :3].astype(np.float64), m[:, 3].astype(np.float64)
+        self.parts = [((p @ R.T + t).astype(np.float32), (n @ np.linalg.inv(R)).astype(np.float32), i) for p, n, i in self.parts]
+        for k, (p, n, i) in enumerate(self.parts):
+            ln = np.linalg.norm(n, axis=1, keepdims=True)
+            self.parts[k] = (p, (n / np.maximum(ln, 1e-30)).astype(np.float32), i)
+        if self.faces:
+            for f in self.faces:
+                f.transform(m)
+
+    def merged(self):
+        return scenes._merge(self.parts)
+
+
+class _Object:
+    def __init__(self, name, shape):
+        self.name = name
+        self.shape = shape
+        self.location = np.eye(3, 4)
+        self.material_name = "default"
+        self.bsdf = NAMED_MATERIALS["default"]()
+        self.displayed = True
+
+
+def _quat_to_mat(x, y, z, w):
+    n = math.sqrt(x * x + y * y + z * z + w * w) or 1.0
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _compose(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """a * b for row-major 3x4 affine matrices."""
+    A, B = np.eye(4), np.eye(4)
+    A[:3], B[:3] = a, b
+    return (A @ B)[:3]
+
+
+class DrawSession(Interp):
+    """Evaluates a script and accumulates the viewer state; `scene()` returns the SceneDesc."""
+
+    SPHERE_RES = (64, 32)
+
+    def __init__(self, width=512, height=512, root: Optional[str] = None):
+        super().__init__()
+        self.width, self.height = width, height
+        self.shapes: Dict[str, _Shape] = {}
+        self.objects: Dict[str, _Object] = {}     # displayed AIS objects, insertion ordered
+        self.lights: List[dict] = [dict(kind="directional", head=True, vec=(0, 0, -1), smooth=0.0, intensity=1.0, color=(1, 1, 1))]
+        self.params = Graphic3d_RenderingParams()
+        self.proj = np.array([0.0, -1.0, 0.0])     # direction from the scene towards the eye
+        self.up = np.array([0.0, 0.0, 1.0])
+        self.at: Optional[np.ndarray] = None
+        self.eye: Optional[np.ndarray] = None
+        self.fovy = 45.0
+        self.ortho = False
+        self.size: Optional[float] = None
+        self.distance: Optional[float] = None
+        self.fit_requested = True
+        self.envmap: Optional[np.ndarray] = None
+        self.frames: Optional[int] = None
+        if root is not None:
+            self.vars["Root"] = root
+        for name in ("box psphere pcylinder compound explode ttranslate trotate tcopy vclear vdisplay verase vremove vlocation "
+                     "vsetmaterial vbsdf vlight rtlight vcamera vviewparams vfront vback vtop vbottom vleft vright vaxo vfit "
+                     "vrenderparams vtextureenv vsetdispmode vinit vfps vdump pload vglinfo vzbufftrihedron vrepaint vupdate").split():
+            self.cmds[name] = getattr(self, "_d_" + name, self._d_ignore)
+
+    def _d_ignore(self, a):
+        return ""
+
+    # -- shapes
+    def _d_box(self, a):
+        v = [float(x) for x in a[1:]]
+        if len(v) == 3:
+            o, d = (0.0, 0.0, 0.0), v
+        elif len(v) == 6:
+            o, d = v[:3], v[3:]
+        else:
+            raise TclError("box name [x y z] dx dy dz")
+        faces = scenes.box_faces(d[0], d[1], d[2], 1, o)
+        s = _Shape([scenes._merge(faces)])
+        s.faces = [_Shape([scenes._merge([f])]) for f in faces]
+        self.shapes[a[0]] = s
+
+    def _d_psphere(self, a):
+        self.shapes[a[0]] = _Shape([scenes.uv_sphere(float(a[1]), *self.SPHERE_RES)])
+
+    def _d_pcylinder(self, a):
+        self.shapes[a[0]] = _Shape([scenes.cylinder(float(a[1]), float(a[2]), seg=64)])
+
+    def _shape(self, name) -> _Shape:
+        if name not in self.shapes:
+            raise TclError(f"shape '{name}' does not exist")
+        return self.shapes[name]
+
+    def _d_compound(self, a):
+        *members, result = a
+        c = _Shape([])
+        c.members = [self._shape(m).copy() for m in members]
+        for m in c.members:
+            c.parts.extend(m.parts)
+        self.shapes[result] = c
+
+    def _d_explode(self, a):
+        s = self._shape(a[0])
+        kind = a[1].upper() if len(a) > 1 else ""
+        if kind in ("FACE", "F") and s.faces:
+            subs = s.faces
+        elif hasattr(s, "members"):
+            subs = s.members
+        else:
+            subs = [s]
+        names = []
+        for k, sub in enumerate(subs, 1):
+            self.shapes[f"{a[0]}_{k}"] = sub.copy()
+            names.append(f"{a[0]}_{k}")
+        return " ".join(names)
+
+    def _d_ttranslate(self, a):
+        *names, dx, dy, dz = a
+        for n in names:
+            self._shape(n).transform(scenes.trsf((float(dx), float(dy), float(dz))))
+
+    def _d_trotate(self, a):
+        *names, x, y, z, dx, dy, dz, ang = a
+        p = np.array([float(x), float(y), float(z)])
+        r = scenes.trsf((0, 0, 0), (float(dx), float(dy), float(dz)), float(ang)).astype(np.float64)
+        r[:, 3] = p - r[:, :3] @ p
+        for n in names:
+            self._shape(n).transform(r)
+
+    def _d_tcopy(self, a):
+        self.shapes[a[1]] = self._shape(a[0]).copy()
+
+    # -- viewer content
+    def _d_vclear(self, a):
+        self.objects.clear()
+
+    def _names(self, a):
+        return [x for x in a if not x.startswith("-")]
+
+    def _d_vdisplay(self, a):
+        for n in self._names(a):
+            if n in self.objects:
+                self.objects[n].displayed = True
+            else:
+                self.objects[n] = _Object(n, self._shape(n))
+
+    def _d_verase(self, a):
+        for n in self._names(a):
+            if n in self.objects:
+                self.objects[n].displayed = False
+
+    def _d_vremove(self, a):
+        for n in self._names(a):
+            self.objects.pop(n, None)
+
+    def _obj(self, name) -> _Object:
+        if name not in self.objects:
+            raise TclError(f"object '{name}' is not displayed")
+        return self.objects[name]
+
+    def _d_vlocation(self, a):
+        obj = self._obj(self._names(a[:1] if not a[0].startswith("-") else a)[0])
+        i = 0
+        while i < len(a):
+            t = a[i].lower()
+            if t in ("-setlocation", "-location"):
+                obj.location[:, 3] = [float(a[i + 1]), float(a[i + 2]), float(a[i + 3])]
+                i += 4
+            elif t == "-rotate":
+                x, y, z, dx, dy, dz, ang = (float(v) for v in a[i + 1:i + 8])
+                r = scenes.trsf((0, 0, 0), (dx, dy, dz), ang).astype(np.float64)
+                p = np.array([x, y, z])
+                r[:, 3] = p - r[:, :3] @ p
+                obj.location = _compose(obj.location, r)      # LocalTransformation() * rotation
+                i += 8
+            elif t in ("-rotation", "-setrotation"):
+                obj.location[:, :3] = _quat_to_mat(*(float(v) for v in a[i + 1:i + 5]))
+                i += 5
+            elif t == "-reset":
+                obj.location = np.eye(3, 4)
+                i += 1
+            else:
+                i += 1
+
+    def _d_vsetmaterial(self, a):
+        names = self._names(a)
+        mat = names[-1].lower()
+        if mat not in NAMED_MATERIALS:
+            raise TclError(f"unknown material '{names[-1]}'")
+        for n in names[:-1]:
+            o = self._obj(n)
+            o.material_name = mat
+            o.bsdf = NAMED_MATERIALS[mat]()
+
+    @staticmethod
+    def _fresnel(a, i):
+        kind = a[i].lower()
+        if kind == "constant":
+            return Graphic3d_Fresnel.CreateConstant(float(a[i + 1])), i + 2
+        if kind == "schlick":
+            return Graphic3d_Fresnel.CreateSchlick(float(a[i + 1]), float(a[i + 2]), float(a[i + 3])), i + 4
+        if kind == "conductor":
+            return Graphic3d_Fresnel.CreateConductor(float(a[i + 1]), float(a[i + 2])), i + 3
+        if kind == "dielectric":
+            return Graphic3d_Fresnel.CreateDielectric(float(a[i + 1])), i + 2
+        raise TclError("unknown Fresnel model " + a[i])
+
+    @staticmethod
+    def _is_num(s):
+        try:
+            float(s)
+            return True
+        except ValueError:
+            return False
+
+    def _color(self, a, i):
+        """1 or 3 numbers after a flag (`-kd 0.85` is the scalar shorthand, Materials.tcl:31)."""
+        vals = []
+        while i < len(a) and len(vals) < 3 and self._is_num(a[i]):
+            vals.append(float(a[i]))
+            i += 1
+        if len(vals) == 1:
+            vals = vals * 3
+        if len(vals) != 3:
+            raise TclError("expected 1 or 3 colour components")
+        return vals, i
+
+    def _d_vbsdf(self, a):
+        o = self._obj(a[0])
+        b = o.bsdf
+        i = 1
+        normalize = False
+        while i < len(a):
+            t = a[i].lower()
+            if t in ("-kc", "-kd", "-ks", "-kt", "-le", "-absorpcolor"):
+                vals, i = self._color(a, i + 1)
+                tgt = {"-kc": b.Kc, "-kd": b.Kd, "-ks": b.Ks, "-kt": b.Kt, "-le": b.Le, "-absorpcolor": b.Absorption}[t]
+                tgt[0:3] = vals
+            elif t == "-baseroughness":
+                b.Ks[3] = float(a[i + 1]); i += 2
+            elif t == "-coatroughness":
+                b.Kc[3] = float(a[i + 1]); i += 2
+            elif t == "-absorpcoeff":
+                b.Absorption[3] = float(a[i + 1]); i += 2
+            elif t == "-coatfresnel":
+                b.FresnelCoat, i = self._fresnel(a, i + 1)
+            elif t == "-basefresnel":
+                b.FresnelBase, i = self._fresnel(a, i + 1)
+            elif t in ("-n", "-normalize"):
+                normalize = True; i += 1
+            elif t in ("-noupdate", "-update"):
+                i += 1
+            else:
+                raise TclError(f"vbsdf: unknown option {a[i]}")
+        if normalize:
+            b.Normalize()
+        return ""
+
+    # -- lights
+    def _d_vlight(self, a):
+        if not a:
+            return ""
+        sub = a[0].lower()
+        if sub == "clear":
+            self.lights = []
+            return ""
+        if sub in ("add", "new"):
+            kind = a[1].lower()
+            l = dict(kind=kind, head=False, vec=(0.0, 0.0, -1.0) if kind == "directional" else (0.0, 0.0, 0.0),
+                     smooth=0.0, intensity=1.0, color=(1.0, 1.0, 1.0))
+            self.lights.append(l)
+            self._light_opts(l, a[2:])
+            return str(len(self.lights) - 1)
+        if sub == "change":
+            self._light_opts(self.lights[int(a[1])], a[2:])
+            return ""
+        if sub in ("del", "delete", "remove"):
+            self.lights.pop(int(a[1]))
+            return ""
+        raise TclError("vlight: unsupported subcommand " + a[0])
+
+    def _light_opts(self, l, a):
+        i = 0
+        while i < len(a):
+            t = a[i].lower().lstrip("-")
+            if t in ("pos", "position", "dir", "direction"):
+                l["vec"] = tuple(float(v) for v in a[i + 1:i + 4]); i += 4
+            elif t in ("sm", "smoothness"):
+                l["smooth"] = float(a[i + 1]); i += 2
+            elif t in ("int", "intensity"):
+                l["intensity"] = float(a[i + 1]); i += 2
+            elif t in ("head", "headlight"):
+                l["head"] = bool(int(a[i + 1])); i += 2
+            elif t in ("color", "colour"):
+                if self._is_num(a[i + 1]):
+                    l["color"] = tuple(float(v) for v in a[i + 1:i + 4]); i += 4
+                else:
+                    i += 2
+            else:
+                i += 1
+
+    def _d_rtlight(self, a):
+        l = self.lights[int(a[0])]
+        self._light_opts(l, a[1:])
+
+    # -- camera
+    def _d_vcamera(self, a):
+        i = 0
+        while i < len(a):
+            t = a[i].lower()
+            if t in ("-persp", "-perspective"):
+                self.ortho = False; i += 1
+            elif t in ("-ortho", "-orthographic"):
+                self.ortho = True; i += 1
+            elif t in ("-fovy", "-fov"):
+                self.fovy = float(a[i + 1]); i += 2
+            elif t in ("-distance", "-dist"):
+                self.distance = float(a[i + 1]); i += 2
+            else:
+                i += 1
+
+    def _d_vviewparams(self, a):
+        i = 0
+        while i < len(a):
+            t = a[i].lower()
+            if t in ("-proj", "-up", "-at", "-eye"):
+                v = np.array([float(x) for x in a[i + 1:i + 4]])
+                setattr(self, t[1:], v)
+                self.fit_requested = False if t in ("-at", "-eye") else self.fit_requested
+                i += 4
+            elif t in ("-size", "-scale"):
+                if t == "-size":
+                    self.size = float(a[i + 1])
+                i += 2
+            else:
+                i += 1
+
+    def _view(self, proj, up):
+        self.proj, self.up = np.array(proj, float), np.array(up, float)
+        self.eye = self.at = None
+        self.fit_requested = True
+
+    def _d_vfront(self, a): self._view((0, -1, 0), (0, 0, 1))
+    def _d_vback(self, a): self._view((0, 1, 0), (0, 0, 1))
+    def _d_vtop(self, a): self._view((0, 0, 1), (0, 1, 0))
+    def _d_vbottom(self, a): self._view((0, 0, -1), (0, -1, 0))
+    def _d_vleft(self, a): self._view((-1, 0, 0), (0, 0, 1))
+    def _d_vright(self, a): self._view((1, 0, 0), (0, 0, 1))
+    def _d_vaxo(self, a): self._view((1, -1, 1), (0, 0, 1))
+
+    def _d_vfit(self, a):
+        self.eye = self.at = None
+        self.fit_requested = True
+
+    def _d_vrenderparams(self, a):
+        i = 0
+        p = self.params
+        while i < len(a):
+            t = a[i].lower()
+            nxt = a[i + 1] if i + 1 < len(a) else ""
+            if t in ("-raydepth", "-reflections") and self._is_num(nxt):
+                p.RaytracingDepth = int(float(nxt)); i += 2
+            elif t in ("-gi", "-ray", "-raytrace", "-shadows", "-refl", "-fsaa", "-rebuildglsl", "-rebuild"):
+                i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
+            elif t in ("-rasterization", "-raster"):
+                raise TclError("rasterization is out of scope: only the path-traced mode is implemented")
+            elif t == "-iss":
+                i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)   # adaptive sampling: not implemented, ignored
+            elif t in ("-maxrad", "-radianceclamping") and self._is_num(nxt):
+                p.RadianceClampingValue = float(nxt); i += 2
+            elif t in ("-twoside", "-twosided"):
+                p.TwoSidedBsdfModels = nxt.lower() not in ("off", "0"); i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
+            elif t in ("-coherent", "-brng"):
+                p.CoherentPathTracingMode = nxt.lower() not in ("off", "0"); i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
+            elif t == "-env":
+                p.UseEnvironmentMapBackground = nxt.lower() not in ("off", "0"); i += 2
+            elif t in ("-aperture",) and self._is_num(nxt):
+                p.CameraApertureRadius = float(nxt); i += 2
+            elif t in ("-focal",) and self._is_num(nxt):
+                p.CameraFocalPlaneDist = float(nxt); i += 2
+            elif t == "-exposure" and self._is_num(nxt):
+                p.Exposure = float(nxt); i += 2
+            elif t == "-whitepoint" and self._is_num(nxt):
+                p.WhitePoint = float(nxt); i += 2
+            elif t == "-tonemapping":
+                p.ToneMappingMethod = Graphic3d_ToneMappingMethod_Filmic if nxt.lower() == "filmic" else 0; i += 2
+            elif t in ("-spp", "-samples") and self._is_num(nxt):
+                p.SamplesPerPixel = int(float(nxt)); i += 2
+            else:
+                i += 1
+
+    def _d_vtextureenv(self, a):
+        if a and a[0].lower() == "off":
+            self.envmap = None
+            return
+        path = a[-1]
+        from PIL import Image
+        if not os.path.exists(path):
+            raise TclError(f"vtextureenv: cannot read '{path}'")
+        self.envmap = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+
+    def _d_vfps(self, a):
+        if a and self._is_num(a[0]):
+            self.frames = int(float(a[0]))
+
+    # -- result
+    def scene(self) -> scenes.SceneDesc:
+        s = scenes.SceneDesc("tcl", width=self.width, height=self.height)
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        for o in self.objects.values():
+            if not o.displayed:
+                continue
+            pos, nrm, idx = o.shape.merged()
+            s.add((pos, nrm, idx), o.location.astype(np.float32), o.bsdf)
+            w = pos.astype(np.float64) @ o.location[:, :3].T + o.location[:, 3]
+            lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+        if not np.isfinite(lo).all():
+            lo, hi = np.zeros(3), np.ones(3)
+        s.params = self.params
+        s.envmap = self.envmap
+        proj = self.proj / np.linalg.norm(self.proj)
+        if self.eye is not None and self.at is not None:
+            eye, at = self.eye, self.at
+        else:
+            at = 0.5 * (lo + hi) if self.at is None else self.at
+            radius = 0.5 * float(np.linalg.norm(hi - lo))
+            if self.distance is not None and not self.fit_requested:
+                dist = self.distance
+            elif self.ortho:
+                dist = 2.0 * radius + 1.0
+            else:
+                half = math.radians(self.fovy) * 0.5
+                aspect = self.width / self.height
+                half_min = math.atan(math.tan(half) * min(1.0, aspect))
+                dist = radius / math.sin(half_min)
+            eye = at + proj * dist
+            if self.size is None:
+                self.size = 2.0 * radius
+        s.camera = Graphic3d_Camera(Eye=tuple(eye), Direction=tuple(np.asarray(at) - np.asarray(eye)), Up=tuple(self.up),
+                                    FOVy=self.fovy, IsOrthographic=self.ortho, Scale=self.size or 1.0)
+        fwd = np.asarray(at) - np.asarray(eye)
+        fwd = fwd / np.linalg.norm(fwd)
+        for l in self.lights:
+            if l["kind"] == "directional":
+                d = fwd if l["head"] else np.array(l["vec"], float)
+                s.lights.append(make_light(False, d, l["color"], l["intensity"], l["smooth"]))
+            elif l["kind"] in ("positional", "spotlight"):
+                p = np.array(l["vec"], float) + (np.asarray(eye) if l["head"] else 0.0)
+                s.lights.append(make_light(True, p, l["color"], l["intensity"], l["smooth"]))
+            # ambient lights have no path-traced counterpart (the GUI hides them, LightSourcesEditor.cxx:157-178)
+        return s
+
+
+def load_script(path: str, width=512, height=512, strict=False) -> DrawSession:
+    sess = DrawSession(width, height, root=os.path.dirname(os.path.abspath(path)))
+    sess.strict = strict
+    with open(path, "r", encoding="utf-8", errors="replace") as f:
+        sess.eval(f.read())
+    return sess

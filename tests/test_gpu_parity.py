@@ -303,3 +303,26 @@ def test_full_size_properties(product_lib):
     s = view.Trace(org, d, any_hit=True)
     assert np.array_equal(n[0] >= 0, s[0] == 0)
     view.Remove()
+
+
+# ------------------------------------------------------------------ script loader + headless run
+
+def test_tcl_script_headless_run_matches_oracle(tmp_path, product_lib, oracle_lib):
+    """`python -m cadrays_b200.run script.tcl N` (the counterpart of CADRays.exe script.tcl N,
+    main.cxx:164-229) writes Output_<script>_<N>.png/.txt; the PNG equals the oracle's Display pass."""
+    from cadrays_b200 import imageio, run, tcl
+    from oracle.oracle_ffi import OracleScene
+    from tests.test_tcl_cpu import SCRIPT
+    script = tmp_path / "Scene.tcl"
+    script.write_text(SCRIPT)
+    assert run.main([str(script), "6", "--size", "96x64", "--out", str(tmp_path), "--hdr", "--spp-per-redraw", "4"]) == 0
+    png = imageio.read_png_rgb8(str(tmp_path / "Output_Scene_6.png"))
+    fps = float((tmp_path / "Output_Scene_6.txt").read_text())
+    assert fps > 0 and (tmp_path / "Output_Scene_6.hdr").exists()
+    desc = tcl.load_script(str(script), 96, 64).scene()
+    view = V3d_View(0)
+    desc.apply(view)
+    orc = OracleScene(view.ExportBVH())
+    orc.configure(desc)
+    assert np.array_equal(png, orc.display(orc.render(96, 64, 6))[::-1])
+    view.Remove()
