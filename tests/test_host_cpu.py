@@ -212,3 +212,17 @@ def test_scene_generators_are_seeded_and_sized():
     assert len(cb.instances) == 9 and cb.lights[0].is_point == 1 and cb.lights[0].smoothness == pytest.approx(0.06)
     ms = scenes.materials_scene(sphere_res=(16, 8))
     assert len(ms.instances) == 144 + 9 and ms.camera.FOVy == 25.0
+
+
+def test_cpp_host_mirror_compiles_and_runs(tmp_path, product_lib):
+    """include/cadrays_b200.hpp (OCCT-named C++ wrapper) against the C-ABI: g++ build + host-only run."""
+    import subprocess
+    exe = tmp_path / "host_mirror_check"
+    lib = REPO / "cadrays_b200" / "libcadrays_b200.so"
+    cmd = ["g++", "-std=c++17", "-Wall", "-Werror", f"-I{REPO / 'include'}", str(REPO / "tests" / "cpp" / "host_mirror_check.cpp"),
+           "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "blob" in r.stdout
