@@ -118,11 +118,13 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = Path(os.environ.get("CADRAYS_B200_LIB", LIB_PATH))     # A/B variants of the same library
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m cadrays_b200.build` "
+            f"{path} is missing: build it with `python -m cadrays_b200.build` "
             "(there is no CPU or PyTorch fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)   # AttributeError if the ABI is incomplete
         fn.restype = res

@@ -35,11 +35,14 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """defines / out: build an A/B variant (e.g. -DCRT_SHADE_MIN_BLOCKS=6) next to the default library;
+    select it at run time with CADRAYS_B200_LIB=<path>."""
+    if out is None and not force and not _stale():
         return LIB_PATH
+    out = out or LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, _sources()), "-lgomp"]
+    cmd = [nvcc, *NVCC_FLAGS, *defines, "-o", str(out), *map(str, _sources()), "-lgomp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -48,9 +51,12 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    p = build_library(force="--force" in sys.argv, verbose=True)
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    p = build_library(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs,
+                      out=Path(outs[0]).resolve() if outs else None)
     print("built", p)

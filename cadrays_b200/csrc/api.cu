@@ -84,7 +84,7 @@ struct crt_context {
   uint32_t width = 0, height = 0;
 
   // device scene
-  DevBuf<float4> d_nodes, d_tri_verts, d_tri_nrm, d_inst, d_mats, d_lights, d_env;
+  DevBuf<float4> d_arena, d_mats, d_lights, d_env;
   DeviceScene ds{};
   DeviceParams dp{};
 
@@ -111,6 +111,7 @@ struct crt_context {
   // environment CRT_TRAVERSAL=static)
   bool persistent = true;
   bool fuse_traversal = true;   // connect(d) + extend(d+1) in one launch (CRT_FUSE=0 disables)
+  bool l2_persist = false;      // L2 access-policy window over the scene arena (CRT_L2_PERSIST=1)
 
   // metrics
   DevBuf<Counters> d_counters;
@@ -236,20 +237,47 @@ uint32_t auto_batch(const crt_context* c)
 
 int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
 {
-  CRT_CUDA(c->d_nodes.ensure(std::max<size_t>(L.nodes.size(), 4)));
-  CRT_CUDA(c->d_tri_verts.ensure(std::max<size_t>(L.tri_verts.size(), 3)));
-  CRT_CUDA(c->d_tri_nrm.ensure(std::max<size_t>(L.tri_nrm.size(), 3)));
-  CRT_CUDA(c->d_inst.ensure(std::max<size_t>(L.inst.size(), 4)));
-  if (!L.nodes.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_nodes.p, L.nodes.data(), L.nodes.size() * 16, cudaMemcpyHostToDevice, c->stream));
-  if (!L.tri_verts.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_verts.p, L.tri_verts.data(), L.tri_verts.size() * 16, cudaMemcpyHostToDevice, c->stream));
-  if (!L.tri_nrm.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_nrm.p, L.tri_nrm.data(), L.tri_nrm.size() * 16, cudaMemcpyHostToDevice, c->stream));
-  if (!L.inst.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_inst.p, L.inst.data(), L.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  // one arena [nodes | triangle vertices | instances | vertex normals]: the traversal working set is
+  // contiguous, so a single L2 access-policy window can cover it
+  auto pad = [](size_t n) { return (n + 15u) & ~(size_t)15u; };   // float4 units, 256-byte sections
+  const size_t n_nodes = pad(std::max<size_t>(L.nodes.size(), 4)), n_verts = pad(std::max<size_t>(L.tri_verts.size(), 3));
+  const size_t n_inst = pad(std::max<size_t>(L.inst.size(), 4)), n_nrm = pad(std::max<size_t>(L.tri_nrm.size(), 3));
+  CRT_CUDA(c->d_arena.ensure(n_nodes + n_verts + n_inst + n_nrm));
+  float4* nodes = c->d_arena.p;
+  float4* verts = nodes + n_nodes;
+  float4* inst = verts + n_verts;
+  float4* nrm = inst + n_inst;
+  if (!L.nodes.empty()) CRT_CUDA(cudaMemcpyAsync(nodes, L.nodes.data(), L.nodes.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.tri_verts.empty()) CRT_CUDA(cudaMemcpyAsync(verts, L.tri_verts.data(), L.tri_verts.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.tri_nrm.empty()) CRT_CUDA(cudaMemcpyAsync(nrm, L.tri_nrm.data(), L.tri_nrm.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!L.inst.empty()) CRT_CUDA(cudaMemcpyAsync(inst, L.inst.data(), L.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
   CRT_CUDA(cudaStreamSynchronize(c->stream));
-  c->ds.nodes = c->d_nodes.p; c->ds.tri_verts = c->d_tri_verts.p; c->ds.tri_nrm = c->d_tri_nrm.p; c->ds.inst = c->d_inst.p;
+  c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
   if (L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
     return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
+  if (c->l2_persist) {
+    // keep nodes + triangle vertices + instance records resident in the 126 MB L2 while gigabytes of
+    // path state stream past them (hit ratio scaled to the set-aside the device allows)
+    cudaDeviceProp prop;
+    CRT_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    const size_t want = (n_nodes + n_verts + n_inst) * sizeof(float4);
+    const size_t window = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+    const size_t setaside = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
+    if (window > 0 && setaside > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
+      cudaStreamAttrValue attr;
+      std::memset(&attr, 0, sizeof attr);
+      attr.accessPolicyWindow.base_ptr = nodes;
+      attr.accessPolicyWindow.num_bytes = window;
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)window);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    } else {
+      cudaGetLastError();
+    }
+  }
   c->has_layout = true;
   return CRT_OK;
 }
@@ -446,6 +474,7 @@ int crt_create(int device_ordinal, crt_context** out)
   c->sm_count = prop.multiProcessorCount;
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
 
   crt_params_default(&c->params);
   std::memset(&c->cam, 0, sizeof c->cam);
@@ -483,7 +512,7 @@ void crt_destroy(crt_context* c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   collect_spans(c);
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-  c->d_nodes.release(); c->d_tri_verts.release(); c->d_tri_nrm.release(); c->d_inst.release();
+  c->d_arena.release();
   c->d_mats.release(); c->d_lights.release(); c->d_env.release();
   c->ray_o.release(); c->ray_d.release(); c->thr.release(); c->rad.release(); c->hit.release();
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();

@@ -71,6 +71,15 @@ struct PathState {
   uint32_t* work_connect;  // [max_depth]
 };
 
+// Path state is streamed once per kernel (gigabytes per wave); the BVH and triangles are re-read by
+// every ray.  State accesses use the streaming cache operators (ld.global.cs / st.global.cs: evict
+// first) so they do not displace scene data from L1/L2.  CRT_STREAMING=0 builds the plain variant.
+#ifndef CRT_STREAMING
+#define CRT_STREAMING 1
+#endif
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return CRT_STREAMING ? __ldcs(p) : *p; }
+template <typename T> __device__ __forceinline__ void st_stream(T* p, const T& v) { if (CRT_STREAMING) __stcs(p, v); else *p = v; }
+
 // ------------------------------------------------------------------ traversal
 
 struct Hit { float t, u, v; int32_t tri; int32_t inst; };
@@ -226,7 +235,13 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 // retire/refill -> walk inner nodes until a leaf reference -> one leaf or instance step.
 // Identical arithmetic and visiting order per ray as traverse<>, so results and work
 // counters are unchanged.  Policy supplies load(index) / store(token, hit, found).
-constexpr uint32_t kChunk = 64;
+#ifndef CRT_CHUNK
+#define CRT_CHUNK 64
+#endif
+#ifndef CRT_TRACE_MIN_BLOCKS
+#define CRT_TRACE_MIN_BLOCKS 1
+#endif
+constexpr uint32_t kChunk = CRT_CHUNK;
 
 // MODE 0: closest hit for every ray, 1: any hit for every ray, 2: per ray (Policy::load says which;
 // used by the fused "connect(d) + extend(d+1)" launch).
@@ -701,6 +716,7 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
   const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
   const uint32_t total = per_sample * n_batch;
   const uint32_t stride = gridDim.x * blockDim.x;
+  const bool aligned = (P.width & 7u) == 0 && (P.height & 3u) == 0;
   for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += stride) {
     const uint32_t slot = base + (threadIdx.x & 31u);
     const uint32_t k = slot / per_sample;
@@ -738,14 +754,19 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
         o = vadd(o, vadd(vscale(cu, r * cs), vscale(cv, r * sn)));
         d = normalize3(vsub(focus, o));
       }
-      st.ray_o[slot] = make_float4(o.x, o.y, o.z, 1.0f);
-      st.ray_d[slot] = make_float4(d.x, d.y, d.z, __int_as_float(0));
-      st.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng));
-      st.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      st_stream(&st.ray_o[slot], make_float4(o.x, o.y, o.z, 1.0f));
+      st_stream(&st.ray_d[slot], make_float4(d.x, d.y, d.z, __int_as_float(0)));
+      st_stream(&st.thr[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng)));
+      st_stream(&st.rad[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     }
-    const uint32_t at = warp_push(st.n_active, valid);
-    if (valid) st.queue[0][at] = slot;
+    if (aligned) {
+      st.queue[0][slot] = slot;             // every slot is a pixel: identity queue, no atomics
+    } else {
+      const uint32_t at = warp_push(st.n_active, valid);
+      if (valid) st.queue[0][at] = slot;
+    }
   }
+  if (aligned && blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = total;
 }
 
 struct ExtendPolicy {
@@ -753,22 +774,22 @@ struct ExtendPolicy {
   const uint32_t* __restrict__ q;
   __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool&) const
   {
-    const uint32_t slot = q[i];
-    const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const uint32_t slot = ld_stream(&q[i]);
+    const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]);
     o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = CRT_MAXFLOAT;
     return slot;
   }
   __device__ __forceinline__ void store(uint32_t slot, const Hit& hit, bool, bool) const
   {
-    st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
-    st.hit_inst[slot] = hit.inst;
+    st_stream(&st.hit[slot], make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri)));
+    st_stream(&st.hit_inst[slot], (int32_t)hit.inst);
   }
 };
 
 // SceneNearestHit for every active path.  PERSISTENT selects the per-lane-refill driver
 // (grid = resident CTAs) or the static one-ray-per-loop-iteration form (kept for A/B).
 template <bool COUNT, bool PERSISTENT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
 k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_active[depth];
@@ -779,13 +800,13 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
     trace_persistent<0, COUNT>(S, n, st.work_extend + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const uint32_t slot = q[i];
-      const float4 o = st.ray_o[slot], d = st.ray_d[slot];
+      const uint32_t slot = ld_stream(&q[i]);
+      const float4 o = ld_stream(&st.ray_o[slot]), d = ld_stream(&st.ray_d[slot]);
       Hit hit;
       traverse<false, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), CRT_MAXFLOAT, hit, cnt);
       if (COUNT) cnt.rays_nearest++;
-      st.hit[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
-      st.hit_inst[slot] = hit.inst;
+      st_stream(&st.hit[slot], make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri)));
+      st_stream(&st.hit_inst[slot], (int32_t)hit.inst);
     }
   }
   if (COUNT) flush_counters(gcnt, cnt);
@@ -795,8 +816,11 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 // light / environment hit with MIS, emission, next-event estimation (emits a
 // shadow ray), Beer-Lambert absorption, layered-BSDF sampling, termination /
 // Russian roulette, continuation ray.
+#ifndef CRT_SHADE_MIN_BLOCKS
+#define CRT_SHADE_MIN_BLOCKS 8
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_active[depth];
@@ -818,9 +842,9 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
     uint32_t rng = 0;
     bool inside = false;
     if (valid) {
-      slot = q[i];
-      const float4 ro = st.ray_o[slot], rd = st.ray_d[slot], tw = st.thr[slot], hh = st.hit[slot];
-      float4 rr = st.rad[slot];
+      slot = ld_stream(&q[i]);
+      const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]), hh = ld_stream(&st.hit[slot]);
+      float4 rr = ld_stream(&st.rad[slot]);
       org = V(ro.x, ro.y, ro.z); dir = V(rd.x, rd.y, rd.z);
       imp_pdf = ro.w;
       inside = (__float_as_int(rd.w) & 1) != 0;
@@ -837,7 +861,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
                         : imp_pdf * imp_pdf / (exp_pdf * exp_pdf + imp_pdf * imp_pdf);
         radiance = vadd(radiance, vscale(vmul(thr, le), mis));
       } else {
-        const int32_t inst = st.hit_inst[slot];
+        const int32_t inst = ld_stream(&st.hit_inst[slot]);
         const float4* ir = S.inst + 4 * (size_t)inst;
         const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
         const v3 c0 = V(m0.x, m1.x, m2.x), c1 = V(m0.y, m1.y, m2.y), c2 = V(m0.z, m1.z, m2.z);
@@ -927,22 +951,24 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
           want_next = true;
         }
       }
-      rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
-      st.rad[slot] = rr;
+      if (radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {
+        rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
+        st_stream(&st.rad[slot], rr);
+      }
     }
     // ---- warp-aggregated queue compaction
     const uint32_t sh_at = warp_push(st.n_shadow + depth, want_shadow);
     if (want_shadow) {
-      st.sh_o[sh_at] = make_float4(sh_o.x, sh_o.y, sh_o.z, sh_tmax);
-      st.sh_d[sh_at] = make_float4(sh_d.x, sh_d.y, sh_d.z, __uint_as_float(slot));
-      st.sh_c[sh_at] = make_float4(sh_c.x, sh_c.y, sh_c.z, 0.0f);
+      st_stream(&st.sh_o[sh_at], make_float4(sh_o.x, sh_o.y, sh_o.z, sh_tmax));
+      st_stream(&st.sh_d[sh_at], make_float4(sh_d.x, sh_d.y, sh_d.z, __uint_as_float(slot)));
+      st_stream(&st.sh_c[sh_at], make_float4(sh_c.x, sh_c.y, sh_c.z, 0.0f));
     }
     const uint32_t nx_at = warp_push(st.n_active + depth + 1, want_next);
     if (want_next) {
-      qn[nx_at] = slot;
-      st.ray_o[slot] = make_float4(org.x, org.y, org.z, imp_pdf);
-      st.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float(inside ? 1 : 0));
-      st.thr[slot] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+      st_stream(&qn[nx_at], slot);
+      st_stream(&st.ray_o[slot], make_float4(org.x, org.y, org.z, imp_pdf));
+      st_stream(&st.ray_d[slot], make_float4(dir.x, dir.y, dir.z, __int_as_float(inside ? 1 : 0)));
+      st_stream(&st.thr[slot], make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng)));
     }
   }
   if (COUNT) flush_counters(gcnt, cnt);
@@ -952,24 +978,24 @@ struct ConnectPolicy {
   PathState st;
   __device__ __forceinline__ uint32_t load(uint32_t i, v3& o, v3& d, float& tmax, bool&) const
   {
-    const float4 ro = st.sh_o[i], rd = st.sh_d[i];
+    const float4 ro = ld_stream(&st.sh_o[i]), rd = ld_stream(&st.sh_d[i]);
     o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); tmax = ro.w;
     return i;
   }
   __device__ __forceinline__ void store(uint32_t i, const Hit&, bool occluded, bool) const
   {
     if (occluded) return;
-    const uint32_t slot = __float_as_uint(st.sh_d[i].w);
-    const float4 c = st.sh_c[i];
-    float4 r = st.rad[slot];
+    const uint32_t slot = __float_as_uint(ld_stream(&st.sh_d[i]).w);
+    const float4 c = ld_stream(&st.sh_c[i]);
+    float4 r = ld_stream(&st.rad[slot]);
     r.x += c.x; r.y += c.y; r.z += c.z;
-    st.rad[slot] = r;
+    st_stream(&st.rad[slot], r);
   }
 };
 
 // SceneAnyHit for the shadow rays of this bounce; visible => add the contribution.
 template <bool COUNT, bool PERSISTENT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
 k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_shadow[depth];
@@ -979,16 +1005,16 @@ k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
     trace_persistent<1, COUNT>(S, n, st.work_connect + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const float4 o = st.sh_o[i], d = st.sh_d[i];
+      const float4 o = ld_stream(&st.sh_o[i]), d = ld_stream(&st.sh_d[i]);
       Hit hit;
       const bool occluded = traverse<true, COUNT>(S, V(o.x, o.y, o.z), V(d.x, d.y, d.z), o.w, hit, cnt);
       if (COUNT) cnt.rays_any++;
       if (!occluded) {
         const uint32_t slot = __float_as_uint(d.w);
-        const float4 c = st.sh_c[i];
-        float4 r = st.rad[slot];
+        const float4 c = ld_stream(&st.sh_c[i]);
+        float4 r = ld_stream(&st.rad[slot]);
         r.x += c.x; r.y += c.y; r.z += c.z;
-        st.rad[slot] = r;
+        st_stream(&st.rad[slot], r);
       }
     }
   }
@@ -1016,7 +1042,7 @@ struct DualPolicy {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
 k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n_ext = st.n_active[depth];
@@ -1040,7 +1066,7 @@ k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_b
     if (px >= P.width || py >= P.height) continue;
     float4 a = accum[(size_t)py * P.width + px];
     for (uint32_t k = 0; k < n_batch; ++k) {
-      const float4 c = st.rad[(size_t)k * per_sample + in];
+      const float4 c = ld_stream(&st.rad[(size_t)k * per_sample + in]);
       a.x += (c.x != c.x) ? 0.0f : minf(c.x, P.max_radiance);
       a.y += (c.y != c.y) ? 0.0f : minf(c.y, P.max_radiance);
       a.z += (c.z != c.z) ? 0.0f : minf(c.z, P.max_radiance);
