@@ -376,7 +376,7 @@ struct Converter {
     if (info[0] < 0) {
       const int64_t first = (int64_t)tri_off + info[1], last = (int64_t)tri_off + info[2];
       if (first < 0 || last < first || last >= (int64_t)v.hdr.n_tris) { err = "blob: leaf range"; ok = false; return kRefNone; }
-      out.tri_verts[3 * (size_t)last + 1].w = bits(1);
+      out.tri_verts[kTriStride * (size_t)last + 1].w = bits(1);
       return (int32_t)(kRefLeafBit | (uint32_t)first);
     }
     if (info[0] != 0) { err = "blob: top-level leaf inside a bottom tree"; ok = false; return kRefNone; }
@@ -460,7 +460,7 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
       for (int64_t t = lo; t < hi; ++t) tri_voff[(size_t)t] = ranges[r].second;
     }
   }
-  out.tri_verts.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
+  out.tri_verts.assign(kTriStride * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
   out.tri_nrm.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
   for (size_t t = 0; t < h.n_tris; ++t) {
     const int32_t* tr = v.tris + 4 * t;
@@ -471,10 +471,10 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
       if (vi < 0 || vi >= (int64_t)h.n_verts) { err = "blob: vertex index"; return false; }
       const float* p = v.vert_pos + 3 * (size_t)vi;
       const float* n = v.vert_nrm + 3 * (size_t)vi;
-      out.tri_verts[3 * t + k] = f4{ p[0], p[1], p[2], 0.0f };
+      out.tri_verts[kTriStride * t + k] = f4{ p[0], p[1], p[2], 0.0f };
       out.tri_nrm[3 * t + k] = f4{ n[0], n[1], n[2], 0.0f };
     }
-    out.tri_verts[3 * t].w = Converter::bits(tr[3]);
+    out.tri_verts[kTriStride * t].w = Converter::bits(tr[3]);
   }
   out.inst.assign(4 * (size_t)h.n_inst, f4{ 0, 0, 0, 0 });
   for (size_t k = 0; k < h.n_inst; ++k) {

@@ -75,6 +75,13 @@ constexpr int32_t  kRefNone    = 0x7fffffff;       // empty scene
 
 struct f4 { float x, y, z, w; };
 
+// float4 records per triangle in tri_verts: 3 = packed 48 B, 4 = padded to 64 B so that a triangle is
+// one aligned 64-byte record (two 256-bit loads).
+#ifndef CRT_TRI_STRIDE
+#define CRT_TRI_STRIDE 3
+#endif
+constexpr size_t kTriStride = CRT_TRI_STRIDE;
+
 // What the kernels walk.  Derived from the blob, never from HostScene, so that
 // crt_bvh_import and crt_commit share one path.
 struct DeviceLayout {
@@ -82,8 +89,8 @@ struct DeviceLayout {
   //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = same for child 1
   //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (ref0, ref1, 0, 0) as int bits
   std::vector<f4> nodes;
-  // 3 x float4 per triangle in blob order: v0.w = caller's triangle index bits,
-  // v1.w = 1 if last triangle of its leaf, v2.w = 0
+  // kTriStride x float4 per triangle in blob order: v0.w = caller's triangle index bits,
+  // v1.w = 1 if last triangle of its leaf, v2.w = 0 (+ one pad float4 when kTriStride == 4)
   std::vector<f4> tri_verts;
   // 3 x float4 per triangle: vertex normals
   std::vector<f4> tri_nrm;

@@ -12,6 +12,7 @@
 // so a whole frame is enqueued without a host round trip.
 #pragma once
 #include "device_math.cuh"
+#include "host_scene.hpp"   // kTriStride, reference encodings
 
 namespace crt {
 
@@ -79,6 +80,33 @@ struct PathState {
 #endif
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return CRT_STREAMING ? __ldcs(p) : *p; }
 template <typename T> __device__ __forceinline__ void st_stream(T* p, const T& v) { if (CRT_STREAMING) __stcs(p, v); else *p = v; }
+
+// 64-byte records (BVH node, instance) are fetched with two 256-bit loads (LDG.E.256, new on
+// sm_100): half the L1 tag lookups of four 128-bit loads for the same bytes.  CRT_LDG256=0 = 4 x 128.
+#ifndef CRT_LDG256
+#define CRT_LDG256 1
+#endif
+__device__ __forceinline__ void ld_record64(const float4* p, float4& a, float4& b, float4& c, float4& d)
+{
+#if CRT_LDG256
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(p + 2));
+#else
+  a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); d = __ldg(p + 3);
+#endif
+}
+
+__device__ __forceinline__ void ld_triangle(const float4* p, float4& a, float4& b, float4& c)
+{
+#if CRT_LDG256 && CRT_TRI_STRIDE == 4
+  float4 pad;
+  ld_record64(p, a, b, c, pad);
+#else
+  a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2);
+#endif
+}
 
 // ------------------------------------------------------------------ traversal
 
@@ -171,7 +199,8 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
     while (cur >= 0) {
       if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
       const float4* nd = S.nodes + 4 * (size_t)cur;
-      const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+      float4 n0, n1, n2, n3;
+        ld_record64(nd, n0, n1, n2, n3);
       const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
       const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
       const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
@@ -199,7 +228,8 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
       if (COUNT) { if (ANY) cnt.n_switch_any++; else cnt.n_switch++; }
       inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
       const float4* ir = S.inst + 4 * (size_t)inst;
-      const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+      float4 m0, m1, m2, m3;
+        ld_record64(ir, m0, m1, m2, m3);
       r.setup(xf_point(m0, m1, m2, org), xf_vector(m0, m1, m2, dir));
       stack[sp++] = kSentinel;
       cur = __float_as_int(m3.x);
@@ -210,8 +240,9 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
       bool more = true;
       while (more) {
         if (COUNT) { if (ANY) cnt.n_tri_any++; else cnt.n_tri++; }
-        const float4* tv = S.tri_verts + 3 * (size_t)tri;
-        const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+        const float4* tv = S.tri_verts + kTriStride * (size_t)tri;
+        float4 a, b, c;
+        ld_triangle(tv, a, b, c);
         float t, u, v;
         more = __float_as_int(b.w) == 0;
         if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
@@ -303,7 +334,8 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
       {
         if (COUNT) { if (any_ray) cnt.n_inner_any++; else cnt.n_inner++; }
         const float4* nd = S.nodes + 4 * (size_t)cur;
-        const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+        float4 n0, n1, n2, n3;
+        ld_record64(nd, n0, n1, n2, n3);
         const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
         const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
         const float c0z0 = fmaf(n2.x, r.inv.z, r.oinv.z), c0z1 = fmaf(n2.y, r.inv.z, r.oinv.z);
@@ -332,7 +364,8 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         if (COUNT) { if (any_ray) cnt.n_switch_any++; else cnt.n_switch++; }
         inst = (int32_t)((uint32_t)cur & 0x3fffffffu);
         const float4* ir = S.inst + 4 * (size_t)inst;
-        const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+        float4 m0, m1, m2, m3;
+        ld_record64(ir, m0, m1, m2, m3);
         r.setup(xf_point(m0, m1, m2, org), xf_vector(m0, m1, m2, dir));
         stack[sp++] = kSentinel;
         cur = __float_as_int(m3.x);
@@ -342,8 +375,9 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         bool more = true;
         while (more) {
           if (COUNT) { if (any_ray) cnt.n_tri_any++; else cnt.n_tri++; }
-          const float4* tv = S.tri_verts + 3 * (size_t)tri;
-          const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+          const float4* tv = S.tri_verts + kTriStride * (size_t)tri;
+          float4 a, b, c;
+          ld_triangle(tv, a, b, c);
           float t, u, v;
           more = __float_as_int(b.w) == 0;
           if (tri_test(r.o, r.d, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), t, u, v) && t < hit.t) {
@@ -863,11 +897,13 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
       } else {
         const int32_t inst = ld_stream(&st.hit_inst[slot]);
         const float4* ir = S.inst + 4 * (size_t)inst;
-        const float4 m0 = __ldg(ir), m1 = __ldg(ir + 1), m2 = __ldg(ir + 2), m3 = __ldg(ir + 3);
+        float4 m0, m1, m2, m3;
+        ld_record64(ir, m0, m1, m2, m3);
         const v3 c0 = V(m0.x, m1.x, m2.x), c1 = V(m0.y, m1.y, m2.y), c2 = V(m0.z, m1.z, m2.z);
         // geometric normal from the stored vertices (same expression as tri_test's nn)
-        const float4* tv = S.tri_verts + 3 * (size_t)tri;
-        const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
+        const float4* tv = S.tri_verts + kTriStride * (size_t)tri;
+        float4 a, b, c;
+        ld_triangle(tv, a, b, c);
         const v3 p0 = V(a.x, a.y, a.z), p1 = V(b.x, b.y, b.z), p2 = V(c.x, c.y, c.z);
         const v3 nraw = cross3(vsub(p0, p2), vsub(p1, p0));
         const v3 ng = normalize3(V(dot3(c0, nraw), dot3(c1, nraw), dot3(c2, nraw)));
@@ -1123,7 +1159,7 @@ struct TracePolicy {
   __device__ __forceinline__ void store(uint32_t i, const Hit& hit, bool f, bool = false) const
   {
     int32_t prim = -1;
-    if (f) prim = ANY ? 0 : __float_as_int(__ldg(tri_verts + 3 * (size_t)hit.tri).w);
+    if (f) prim = ANY ? 0 : __float_as_int(__ldg(tri_verts + kTriStride * (size_t)hit.tri).w);
     hit4[i] = make_float4(hit.t, hit.u, hit.v, __int_as_float(prim));
     if (hit_inst) hit_inst[i] = hit.inst;
   }
