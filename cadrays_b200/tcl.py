@@ -9,6 +9,7 @@ substitution, braces and quotes) plus the DRAW / ViewerTest commands those scrip
   viewer   vclear vdisplay verase vremove vlocation vsetmaterial vbsdf vlight rtlight vcamera vviewparams
            vfront vback vtop vbottom vleft vright vaxo vfit vrenderparams vtextureenv vsetdispmode
            vinit vfps vdump(ignored)
+  CADRays  rtmeshread (PLY, the exporter's mesh format) rtdisplay rterase
 
 Everything produces a cadrays_b200.scenes.SceneDesc; rendering stays in libcadrays_b200.so.
 Default BSDFs of OCCT's named materials (`vsetmaterial <obj> glass`) live in the absent
@@ -473,7 +474,8 @@ class DrawSession(Interp):
             self.vars["Root"] = root
         for name in ("box psphere pcylinder compound explode ttranslate trotate tcopy vclear vdisplay verase vremove vlocation "
                      "vsetmaterial vbsdf vlight rtlight vcamera vviewparams vfront vback vtop vbottom vleft vright vaxo vfit "
-                     "vrenderparams vtextureenv vsetdispmode vinit vfps vdump pload vglinfo vzbufftrihedron vrepaint vupdate").split():
+                     "vrenderparams vtextureenv vsetdispmode vinit vfps vdump pload vglinfo vzbufftrihedron vrepaint vupdate "
+                     "rtmeshread rtdisplay rterase").split():
             self.cmds[name] = getattr(self, "_d_" + name, self._d_ignore)
 
     def _d_ignore(self, a):
@@ -542,6 +544,42 @@ class DrawSession(Interp):
 
     def _d_tcopy(self, a):
         self.shapes[a[1]] = self._shape(a[0]).copy()
+
+    # -- CADRays' own DRAW commands (src/ImportExport/ImportExportPlugin.cxx:973-994), mesh subset
+    def _d_rtmeshread(self, a):
+        """rtmeshread <file> <name> [-group] [-up X|Y|Z|-X|-Y|-Z] ...: PLY files as the exporter writes them."""
+        from . import ply
+        path, name = a[0], a[1]
+        if not os.path.exists(path):
+            raise TclError(f"rtmeshread: cannot read '{path}'")
+        if not path.lower().endswith(".ply"):
+            raise TclError("rtmeshread: only PLY meshes are supported (the exporter's format); OBJ/FBX need Assimp")
+        pos, nrm, uv, idx = ply.read_ply(path)
+        up = None
+        for k, t in enumerate(a):
+            if t.lower() == "-up" and k + 1 < len(a):
+                up = a[k + 1].upper()
+        if up in ("Y", "-Y"):                      # MeshImporter's axis flip to the viewer's Z-up
+            sgn = 1.0 if up == "Y" else -1.0
+            rot = np.array([[1, 0, 0], [0, 0, -sgn], [0, sgn, 0]], dtype=np.float32)
+            pos = pos @ rot.T
+            nrm = None if nrm is None else nrm @ rot.T
+        if nrm is None:
+            e0, e1 = pos[idx[:, 1]] - pos[idx[:, 0]], pos[idx[:, 2]] - pos[idx[:, 0]]
+            fn = np.cross(e0, e1)
+            acc = np.zeros_like(pos, dtype=np.float64)
+            for k in range(3):
+                np.add.at(acc, idx[:, k], fn)
+            ln = np.linalg.norm(acc, axis=1, keepdims=True)
+            nrm = np.where(ln > 0, acc / np.maximum(ln, 1e-30), [0, 0, 1]).astype(np.float32)
+        self.shapes[name] = _Shape([(pos.astype(np.float32), nrm.astype(np.float32), idx.astype(np.uint32))])
+        return name
+
+    def _d_rtdisplay(self, a):
+        self._d_vdisplay(a)
+
+    def _d_rterase(self, a):
+        self._d_verase(a)
 
     # -- viewer content
     def _d_vclear(self, a):

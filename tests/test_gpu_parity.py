@@ -326,3 +326,17 @@ def test_tcl_script_headless_run_matches_oracle(tmp_path, product_lib, oracle_li
     orc.configure(desc)
     assert np.array_equal(png, orc.display(orc.render(96, 64, 6))[::-1])
     view.Remove()
+
+
+def test_level3_converged_4096spp(product_lib, oracle_lib):
+    """north_star level 3: converged 4096-spp images.  Stated bound: per-pixel relative error <= 1e-5 and
+    RMSE <= 1e-6 of the mean; measured: bit-equal (same sample set, same summation order)."""
+    desc = scenes.cornell_box(24, 16, depth=5, sphere_res=(16, 8))
+    view, orc = _pair(desc)
+    view.Redraw(4096)
+    g = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    o = orc.hdr(orc.render(24, 16, 4096))
+    rel = np.abs(g - o) / np.maximum(np.abs(o), 1e-6)
+    assert rel.max() <= 1e-5 and float(np.sqrt(np.mean((g - o) ** 2))) <= 1e-6 * float(o.mean())
+    assert np.array_equal(g, o)
+    view.Remove()

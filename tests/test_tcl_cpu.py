@@ -173,3 +173,42 @@ def test_image_writers_roundtrip(tmp_path):
     body = np.frombuffer(raw[raw.index(b"+X 4\n") + 5:], dtype=np.uint8).reshape(6, 4, 4)
     dec = body[..., :3].astype(np.float64) * np.ldexp(1.0, body[..., 3].astype(np.int32) - 136)[..., None]
     assert np.allclose(dec, hdr[::-1], rtol=0.02, atol=0.05)
+
+
+def test_ply_roundtrip_and_exported_model(tmp_path):
+    """The exporter writes model.tcl + meshes/*.ply (binary PLY) and reloads them with rtmeshread
+    (ImportExport.cxx:84-93): a scene saved in that grammar loads back."""
+    from cadrays_b200 import ply
+    pos, nrm, idx = scenes.uv_sphere(1.0, 12, 6)
+    (tmp_path / "meshes").mkdir()
+    ply.write_ply(str(tmp_path / "meshes" / "Ball.ply"), pos, nrm, idx, binary=True)
+    ply.write_ply(str(tmp_path / "meshes" / "BallAscii.ply"), pos, None, idx, binary=False)
+    p2, n2, uv2, i2 = ply.read_ply(str(tmp_path / "meshes" / "Ball.ply"))
+    assert np.array_equal(p2, pos) and np.array_equal(n2, nrm) and np.array_equal(i2, idx) and uv2 is None
+    p3, n3, _, i3 = ply.read_ply(str(tmp_path / "meshes" / "BallAscii.ply"))
+    assert np.allclose(p3, pos) and n3 is None and np.array_equal(i3, idx)
+    model = tmp_path / "model.tcl"
+    model.write_text("""
+vclear
+rtmeshread $Root/meshes/Ball.ply Ball -group
+rtdisplay Ball
+vsetmaterial Ball Gold -noupdate
+vbsdf Ball -Kd 0.1 0.1 0.1 -noupdate
+vlocation Ball -rotation 0 0 0.7071068 0.7071068
+vlocation Ball -location 1 2 3
+rtmeshread $Root/meshes/BallAscii.ply B2
+vdisplay B2 -noupdate
+vcamera -orthographic
+vviewparams -proj 1 -1 1 -up 0 0 1 -at 0 0 0 -eye 10 -10 10 -size 12.5
+vlight clear
+vlight add positional position 5 5 5 head 0 smoothness 0.2 intensity 40
+""")
+    d = tcl.load_script(str(model), 64, 64, strict=True).scene()
+    assert len(d.instances) == 2 and d.meshes[0][2].shape == idx.shape
+    xf = d.instances[0][1]
+    assert np.allclose(xf[:, 3], [1, 2, 3]) and np.allclose(xf[:, :3], [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-6)
+    assert d.camera.IsOrthographic and d.camera.Scale == 12.5
+    assert np.allclose(np.linalg.norm(d.meshes[1][1], axis=1), 1.0, atol=1e-5)     # synthesised normals
+    assert d.lights[0].is_point == 1 and d.lights[0].smoothness == pytest.approx(0.2)
+    with pytest.raises(tcl.TclError):
+        tcl.load_script(str(model), 8, 8).eval("rtmeshread /nonexistent.ply X")
