@@ -207,25 +207,35 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     any_uv = any_uv || scene.meshes[mi].has_uv;
   }
 
-  // top-level tree over instance world boxes (8 transformed corners of the mesh root box)
+  // top-level tree over instance world boxes.  OCCT transforms the 8 corners of the bottom root box;
+  // here the box is the tight one of the transformed vertices (rotated parts get up to ~1.7x smaller
+  // boxes => fewer false instance entries), padded by a few ulps because the traversal intersects in
+  // object space with a differently rounded transform.  Visiting order only; hits are unaffected.
   std::vector<Prim> iprims(n_inst);
   std::vector<float> inv(16 * n_inst);
-  for (size_t k = 0; k < n_inst; ++k) {
+  bool bad_xf = false;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (long k = 0; k < (long)n_inst; ++k) {
     const Instance& in = scene.instances[k];
-    if (!invert_affine(in.xf, &inv[16 * k])) { err = "instance transform is singular"; return false; }
-    const TreeNode& root = trees[in.mesh].nodes[0];
+    if (!invert_affine(in.xf, &inv[16 * k])) { bad_xf = true; continue; }
+    const Mesh& m = scene.meshes[in.mesh];
     Box b;
-    for (int c = 0; c < 8; ++c) {
-      float p[3] = { (c & 1) ? root.hi[0] : root.lo[0], (c & 2) ? root.hi[1] : root.lo[1], (c & 4) ? root.hi[2] : root.lo[2] };
+    const size_t nv = m.pos.size() / 3;
+    for (size_t v = 0; v < nv; ++v) {
+      const float* p = &m.pos[3 * v];
       float q[3];
       for (int r = 0; r < 3; ++r)
         q[r] = in.xf[4 * r] * p[0] + in.xf[4 * r + 1] * p[1] + in.xf[4 * r + 2] * p[2] + in.xf[4 * r + 3];
       b.grow_pt(q);
     }
     Prim& p = iprims[k];
-    for (int r = 0; r < 3; ++r) { p.lo[r] = b.lo[r]; p.hi[r] = b.hi[r]; p.c[r] = 0.5f * (b.lo[r] + b.hi[r]); }
+    for (int r = 0; r < 3; ++r) {
+      const float pad = 4.0e-6f * (std::max(std::fabs(b.lo[r]), std::fabs(b.hi[r])) + (b.hi[r] - b.lo[r])) + 1.0e-30f;
+      p.lo[r] = b.lo[r] - pad; p.hi[r] = b.hi[r] + pad; p.c[r] = 0.5f * (b.lo[r] + b.hi[r]);
+    }
     p.id = (uint32_t)k;
   }
+  if (bad_xf) { err = "instance transform is singular"; return false; }
   std::vector<TreeNode> top;
   int top_depth = 0;
   build_tree(iprims, kTopLeafSize, kTopBins, top, top_depth);

@@ -113,6 +113,13 @@ def test_bvh_blob_is_well_formed(which, product_lib):
             assert x > 0 and x - 1 not in seen_inst
             seen_inst.add(x - 1)
             assert b["meta"][x - 1][2] == y
+            # the (tight, padded) world box of the instance contains every transformed vertex
+            m, xf, _ = desc.instances[x - 1]
+            M = np.eye(3, 4) if xf is None else np.asarray(xf, np.float64)
+            wpos = desc.meshes[m][0].astype(np.float64) @ M[:, :3].T + M[:, 3]
+            assert (wpos >= bmin[n] - 1e-7).all() and (wpos <= bmax[n] + 1e-7).all()
+            ext = wpos.max(0) - wpos.min(0)
+            assert ((bmax[n] - bmin[n]) <= ext * 1.001 + 1e-4).all()      # and is tight
     assert seen_inst == set(range(hdr["n_inst"]))
     # bottom level, per distinct mesh: leaves partition the triangle range, leaf size <= 5,
     # every triangle inside its leaf box, children inside parents
