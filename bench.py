@@ -203,7 +203,9 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcadrays_b200 has no CPU fallback")
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner out of the one-JSON-line stdout
+    # NCCL logs (version banner included) go to stdout by default: send them to stderr so that stdout
+    # carries exactly one JSON line whatever NCCL_DEBUG level the caller chose
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local, world = D.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world
