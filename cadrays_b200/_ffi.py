@@ -80,6 +80,8 @@ PROTOTYPES = {
     "crt_instance_set_material": (C.c_int, [_ctx, C.c_uint32, C.c_uint32]),
     "crt_scene_clear": (C.c_int, [_ctx]),
     "crt_materials_set": (C.c_int, [_ctx, C.POINTER(crt_bsdf), C.c_uint32]),
+    "crt_texture_create": (C.c_int, [_ctx, _u8, C.c_uint32, C.c_uint32, _u32]),
+    "crt_textures_clear": (C.c_int, [_ctx]),
     "crt_lights_set": (C.c_int, [_ctx, C.POINTER(crt_light), C.c_uint32]),
     "crt_envmap_set_rgb8": (C.c_int, [_ctx, _u8, C.c_uint32, C.c_uint32]),
     "crt_envmap_set_rgb32f": (C.c_int, [_ctx, _f, C.c_uint32, C.c_uint32]),

@@ -78,13 +78,18 @@ struct crt_context {
   std::vector<float> lights;         // 8 floats per light, shader form
   std::vector<float> env;            // rgba per texel
   uint32_t env_w = 0, env_h = 0;
-  bool mats_dirty = true, lights_dirty = true, env_dirty = true;
+  std::vector<uint8_t> tex_texels;   // RGBA8 of all textures, back to back
+  std::vector<uint32_t> tex_table;   // offset, width, height per texture
+  bool mats_dirty = true, lights_dirty = true, env_dirty = true, tex_dirty = true;
   crt_params params;
   crt_camera cam;
   uint32_t width = 0, height = 0;
 
   // device scene
   DevBuf<float4> d_arena, d_mats, d_lights, d_env;
+  DevBuf<float2> d_tri_uv;
+  DevBuf<uchar4> d_tex;
+  DevBuf<uint32_t> d_tex_table;
   DeviceScene ds{};
   DeviceParams dp{};
 
@@ -251,7 +256,10 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
   if (!L.tri_verts.empty()) CRT_CUDA(cudaMemcpyAsync(verts, L.tri_verts.data(), L.tri_verts.size() * 16, cudaMemcpyHostToDevice, c->stream));
   if (!L.tri_nrm.empty()) CRT_CUDA(cudaMemcpyAsync(nrm, L.tri_nrm.data(), L.tri_nrm.size() * 16, cudaMemcpyHostToDevice, c->stream));
   if (!L.inst.empty()) CRT_CUDA(cudaMemcpyAsync(inst, L.inst.data(), L.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CRT_CUDA(c->d_tri_uv.ensure(std::max<size_t>(L.tri_uv.size() / 2, 3)));
+  if (!L.tri_uv.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_uv.p, L.tri_uv.data(), L.tri_uv.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CRT_CUDA(cudaStreamSynchronize(c->stream));
+  c->ds.tri_uv = c->d_tri_uv.p;
   c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
@@ -307,6 +315,16 @@ int upload_tables(crt_context* c)
       CRT_CUDA(cudaMemcpyAsync(c->d_lights.p, c->lights.data(), c->lights.size() * 4, cudaMemcpyHostToDevice, c->stream));
     c->ds.lights = c->d_lights.p; c->ds.n_lights = (uint32_t)(c->lights.size() / 8);
     c->lights_dirty = false;
+  }
+  if (c->tex_dirty) {
+    CRT_CUDA(c->d_tex.ensure(std::max<size_t>(c->tex_texels.size() / 4, 1)));
+    CRT_CUDA(c->d_tex_table.ensure(std::max<size_t>(c->tex_table.size(), 3)));
+    if (!c->tex_texels.empty())
+      CRT_CUDA(cudaMemcpyAsync(c->d_tex.p, c->tex_texels.data(), c->tex_texels.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!c->tex_table.empty())
+      CRT_CUDA(cudaMemcpyAsync(c->d_tex_table.p, c->tex_table.data(), c->tex_table.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    c->ds.tex_data = c->d_tex.p; c->ds.tex_table = c->d_tex_table.p; c->ds.n_tex = (uint32_t)(c->tex_table.size() / 3);
+    c->tex_dirty = false;
   }
   if (c->env_dirty) {
     CRT_CUDA(c->d_env.ensure(std::max<size_t>(c->env.size() / 4, 1)));
@@ -512,7 +530,7 @@ void crt_destroy(crt_context* c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   collect_spans(c);
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-  c->d_arena.release();
+  c->d_arena.release(); c->d_tri_uv.release(); c->d_tex.release(); c->d_tex_table.release();
   c->d_mats.release(); c->d_lights.release(); c->d_env.release();
   c->ray_o.release(); c->ray_d.release(); c->thr.release(); c->rad.release(); c->hit.release();
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();
@@ -612,6 +630,29 @@ int crt_materials_set(crt_context* c, const crt_bsdf* b, uint32_t n)
   CRT_REQUIRE(c && (b || n == 0), "null argument");
   c->mats.assign(b, b + n);
   c->mats_dirty = true;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_texture_create(crt_context* c, const uint8_t* rgba8, uint32_t w, uint32_t h, uint32_t* out_id)
+{
+  CRT_REQUIRE(c && rgba8 && out_id, "null argument");
+  CRT_REQUIRE(w > 0 && h > 0 && (uint64_t)w * h < (1ull << 28), "bad texture size");
+  const size_t offset = c->tex_texels.size() / 4;
+  CRT_REQUIRE(offset + (size_t)w * h < (1ull << 31), "texture storage exhausted");
+  c->tex_texels.insert(c->tex_texels.end(), rgba8, rgba8 + (size_t)4 * w * h);
+  c->tex_table.push_back((uint32_t)offset); c->tex_table.push_back(w); c->tex_table.push_back(h);
+  *out_id = (uint32_t)(c->tex_table.size() / 3) - 1;
+  c->tex_dirty = true;
+  reset_accum_state(c);
+  return CRT_OK;
+}
+
+int crt_textures_clear(crt_context* c)
+{
+  CRT_REQUIRE(c, "null context");
+  c->tex_texels.clear(); c->tex_table.clear();
+  c->tex_dirty = true;
   reset_accum_state(c);
   return CRT_OK;
 }

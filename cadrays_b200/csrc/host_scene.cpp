@@ -472,6 +472,7 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
   }
   out.tri_verts.assign(kTriStride * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
   out.tri_nrm.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
+  out.tri_uv.assign(6 * (size_t)h.n_tris, 0.0f);
   for (size_t t = 0; t < h.n_tris; ++t) {
     const int32_t* tr = v.tris + 4 * t;
     const int32_t vo = tri_voff[t];
@@ -483,6 +484,8 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
       const float* n = v.vert_nrm + 3 * (size_t)vi;
       out.tri_verts[kTriStride * t + k] = f4{ p[0], p[1], p[2], 0.0f };
       out.tri_nrm[3 * t + k] = f4{ n[0], n[1], n[2], 0.0f };
+      out.tri_uv[6 * t + 2 * k] = v.vert_uv[2 * (size_t)vi];
+      out.tri_uv[6 * t + 2 * k + 1] = v.vert_uv[2 * (size_t)vi + 1];
     }
     out.tri_verts[kTriStride * t].w = Converter::bits(tr[3]);
   }

@@ -94,6 +94,8 @@ struct DeviceLayout {
   std::vector<f4> tri_verts;
   // 3 x float4 per triangle: vertex normals
   std::vector<f4> tri_nrm;
+  // 6 floats per triangle: (u,v) of the three vertices (zeros when the mesh has no texels)
+  std::vector<float> tri_uv;
   // 4 x float4 per instance: 3 rows of the inverse matrix, then (rootRef, material, 0, 0) bits
   std::vector<f4> inst;
   int32_t top_root = kRefNone;

@@ -7,9 +7,13 @@
 //
 // Design: wavefront.  Path state lives in SoA float4 arrays indexed by path slot;
 // compacted queues of slot indices are produced with warp-aggregated atomics
-// (__ballot_sync + __popc, one atomicAdd per warp).  Kernels are launched with a
-// fixed grid sized from the SM count and read the queue length from device memory,
-// so a whole frame is enqueued without a host round trip.
+// (__ballot_sync + __popc, one atomicAdd per warp).  Kernels read the queue length
+// from device memory, so a whole wave is enqueued without a host round trip.
+// Traversal kernels are persistent (grid = SM count x resident CTAs): each lane
+// pulls its next ray from a warp-local pool as soon as its ray finishes
+// (trace_persistent); shading kernels grid-stride with a grid that is a multiple
+// of the SM count.  One wave:
+//   k_generate -> k_extend(0) -> k_shade(0) -> [k_trace_dual(d) -> k_shade(d)]... -> k_connect -> k_resolve
 #pragma once
 #include "device_math.cuh"
 #include "host_scene.hpp"   // kTriStride, reference encodings
@@ -28,6 +32,10 @@ struct DeviceScene {
   const float4* __restrict__ mats;        // 8 x float4 per material (crt_bsdf)
   const float4* __restrict__ lights;      // 2 x float4 per light (shader form)
   const float4* __restrict__ env;         // lat-long texels, rgb_
+  const float2* __restrict__ tri_uv;      // 3 x float2 per triangle
+  const uchar4* __restrict__ tex_data;    // RGBA8 texels of all base-colour textures
+  const uint32_t* __restrict__ tex_table; // offset, width, height per texture
+  uint32_t n_tex;
   int32_t top_root;
   uint32_t n_mats, n_lights, env_w, env_h;
   float scene_eps;
@@ -659,6 +667,31 @@ __device__ __forceinline__ v3 env_lookup(const DeviceScene& S, v3 d)
   return vadd(vscale(top, 1.0f - ay), vscale(bot, ay));
 }
 
+// textureLod(sampler, st, 0) with GL_LINEAR / GL_REPEAT, t = 0 at the bottom row of the image file.
+__device__ __forceinline__ float4 tex_lookup(const DeviceScene& S, uint32_t tex, float u, float v)
+{
+  const uint32_t off = __ldg(S.tex_table + 3 * tex);
+  const int w = (int)__ldg(S.tex_table + 3 * tex + 1), h = (int)__ldg(S.tex_table + 3 * tex + 2);
+  const float fx = fmaf(u, (float)w, -0.5f);
+  const float fy = fmaf(1.0f - v, (float)h, -0.5f);
+  const float flx = floorf(fx), fly = floorf(fy);
+  const float ax = fx - flx, ay = fy - fly;
+  int x0 = (int)flx, y0 = (int)fly;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = ((x0 % w) + w) % w; x1 = ((x1 % w) + w) % w;
+  y0 = ((y0 % h) + h) % h; y1 = ((y1 % h) + h) % h;
+  const uchar4* t = S.tex_data + off;
+  const uchar4 q00 = __ldg(t + y0 * w + x0), q10 = __ldg(t + y0 * w + x1);
+  const uchar4 q01 = __ldg(t + y1 * w + x0), q11 = __ldg(t + y1 * w + x1);
+  const float k = 1.0f / 255.0f;
+  float4 r;
+#define CRT_BILERP(f) (((float)q00.f * k * (1.0f - ax) + (float)q10.f * k * ax) * (1.0f - ay) + \
+                       ((float)q01.f * k * (1.0f - ax) + (float)q11.f * k * ax) * ay)
+  r.x = CRT_BILERP(x); r.y = CRT_BILERP(y); r.z = CRT_BILERP(z); r.w = CRT_BILERP(w);
+#undef CRT_BILERP
+  return r;
+}
+
 // IntersectLight, SURVEY A.7.
 __device__ __forceinline__ v3 intersect_light(const DeviceScene& S, const DeviceParams& P, v3 o, v3 d, int depth,
                                               float hit_dist, float& pdf_out)
@@ -937,6 +970,26 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
           mat_le = V(0, 0, 0); absorp = V(0, 0, 0); absorp_k = 0.0f;
         }
         if (COUNT) cnt.shaded_hits++;
+
+        // base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV)
+        if (mat_id < S.n_mats) {
+          const float kd_w = __ldg(S.mats + 8 * (size_t)mat_id + 1).w;
+          if (kd_w >= 1.0f && (uint32_t)kd_w - 1u < S.n_tex) {
+            const float2* tu = S.tri_uv + 3 * (size_t)tri;
+            const float2 uv0 = __ldg(tu), uv1 = __ldg(tu + 1), uv2 = __ldg(tu + 2);
+            const float w0 = (1.0f - hh.y) - hh.z;
+            const float su = (uv1.x * hh.y + uv2.x * hh.z) + uv0.x * w0;
+            const float sv = (uv1.y * hh.y + uv2.y * hh.z) + uv0.y * w0;
+            const float kt_w = __ldg(S.mats + 8 * (size_t)mat_id + 3).w, le_w = __ldg(S.mats + 8 * (size_t)mat_id + 4).w;
+            const float ss = kt_w != 0.0f ? kt_w : 1.0f, ts = le_w != 0.0f ? le_w : 1.0f;
+            const float4 tc = tex_lookup(S, (uint32_t)kd_w - 1u, su * ss, sv * ts);
+            B.Kd = vmul(B.Kd, vscale(V(tc.x * tc.x, tc.y * tc.y, tc.z * tc.z), tc.w));
+            if (tc.w != 1.0f) {
+              const float ia = 1.0f - tc.w;
+              B.Kt = V(ia + tc.w * B.Kt.x, ia + tc.w * B.Kt.y, ia + tc.w * B.Kt.z);
+            }
+          }
+        }
 
         const v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), frame);
         radiance = vadd(radiance, vmul(thr, mat_le));

@@ -103,17 +103,21 @@ def read_ply(path: str) -> Tuple[np.ndarray, Optional[np.ndarray], Optional[np.n
     return pos, nrm, uv, idx
 
 
-def write_ply(path: str, pos, nrm, idx, binary: bool = True) -> None:
+def write_ply(path: str, pos, nrm, idx, binary: bool = True, uv=None) -> None:
     pos = np.asarray(pos, np.float32); idx = np.asarray(idx, np.uint32)
     has_n = nrm is not None
     hdr = ["ply", "format " + ("binary_little_endian 1.0" if binary else "ascii 1.0"), f"element vertex {pos.shape[0]}",
            "property float x", "property float y", "property float z"]
     if has_n:
         hdr += ["property float nx", "property float ny", "property float nz"]
+    if uv is not None:
+        hdr += ["property float s", "property float t"]
     hdr += [f"element face {idx.shape[0]}", "property list uchar uint vertex_index", "end_header"]
     with open(path, "wb") as f:
         f.write(("\n".join(hdr) + "\n").encode())
         v = np.hstack([pos, np.asarray(nrm, np.float32)]) if has_n else pos
+        if uv is not None:
+            v = np.hstack([v, np.asarray(uv, np.float32)])
         if binary:
             f.write(v.astype("<f4").tobytes())
             for t in idx:

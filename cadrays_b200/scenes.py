@@ -185,6 +185,8 @@ class SceneDesc:
     width: int = 512
     height: int = 512
     envmap: Optional[np.ndarray] = None
+    textures: List[np.ndarray] = field(default_factory=list)   # uint8 (h,w,3|4), referenced by Graphic3d_BSDF.TextureId
+    mesh_uvs: dict = field(default_factory=dict)                # mesh index -> (n,2) float32 texel coordinates
 
     def add(self, mesh, xf=None, bsdf: Optional[Graphic3d_BSDF] = None, material_id: Optional[int] = None) -> int:
         self.meshes.append(mesh)
@@ -200,7 +202,10 @@ class SceneDesc:
     def apply(self, view: V3d_View, with_target: bool = True):
         """Feeds the scene through the host mirror (and so through the C-ABI)."""
         view.Clear()
-        ids = [view.AddMesh(p, i, n) for (p, n, i) in self.meshes]
+        view.ClearTextures()
+        for t in self.textures:
+            view.AddTexture(t)
+        ids = [view.AddMesh(p, i, n, self.mesh_uvs.get(k)) for k, (p, n, i) in enumerate(self.meshes)]
         for m, xf, mat in self.instances:
             view.Display(ids[m], xf, mat)
         view.SetMaterials(self.materials)

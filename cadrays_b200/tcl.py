@@ -400,10 +400,12 @@ class _Shape:
 
     def __init__(self, parts):
         self.parts = parts          # list of (pos, nrm, idx)
+        self.uvs = [None] * len(parts)   # texel coordinates per part (PLY meshes), or None
         self.faces = None           # for `explode <box> FACE`
 
     def copy(self):
         s = _Shape([(p.copy(), n.copy(), i.copy()) for p, n, i in self.parts])
+        s.uvs = [None if u is None else u.copy() for u in self.uvs]
         if self.faces:
             s.faces = [f.copy() for f in self.faces]
         return s
@@ -420,6 +422,12 @@ class _Shape:
 
     def merged(self):
         return scenes._merge(self.parts)
+
+    def merged_uv(self):
+        if all(u is None for u in self.uvs):
+            return None
+        return np.concatenate([np.zeros((p.shape[0], 2), np.float32) if u is None else u.astype(np.float32)
+                               for (p, _, _), u in zip(self.parts, self.uvs)])
 
 
 class _Object:
@@ -469,13 +477,15 @@ class DrawSession(Interp):
         self.distance: Optional[float] = None
         self.fit_requested = True
         self.envmap: Optional[np.ndarray] = None
+        self.textures: List[np.ndarray] = []
+        self._texture_ids: Dict[str, int] = {}
         self.frames: Optional[int] = None
         if root is not None:
             self.vars["Root"] = root
         for name in ("box psphere pcylinder compound explode ttranslate trotate tcopy vclear vdisplay verase vremove vlocation "
                      "vsetmaterial vbsdf vlight rtlight vcamera vviewparams vfront vback vtop vbottom vleft vright vaxo vfit "
                      "vrenderparams vtextureenv vsetdispmode vinit vfps vdump pload vglinfo vzbufftrihedron vrepaint vupdate "
-                     "rtmeshread rtdisplay rterase").split():
+                     "rtmeshread rtdisplay rterase rttexture vtexture").split():
             self.cmds[name] = getattr(self, "_d_" + name, self._d_ignore)
 
     def _d_ignore(self, a):
@@ -512,6 +522,7 @@ class DrawSession(Interp):
         c.members = [self._shape(m).copy() for m in members]
         for m in c.members:
             c.parts.extend(m.parts)
+            c.uvs.extend(m.uvs)
         self.shapes[result] = c
 
     def _d_explode(self, a):
@@ -573,7 +584,34 @@ class DrawSession(Interp):
             ln = np.linalg.norm(acc, axis=1, keepdims=True)
             nrm = np.where(ln > 0, acc / np.maximum(ln, 1e-30), [0, 0, 1]).astype(np.float32)
         self.shapes[name] = _Shape([(pos.astype(np.float32), nrm.astype(np.float32), idx.astype(np.uint32))])
+        self.shapes[name].uvs = [uv]
         return name
+
+    def _d_rttexture(self, a):
+        """rttexture <node> [<file>] [-scale S T] [-on|-off]  (ImportExportPlugin.cxx:610-750; exporter
+        ImportExport.cxx:259-264); vtexture <node> <file> -scale S T is the AIS_TexturedShape spelling."""
+        o = self._obj(a[0])
+        i = 1
+        while i < len(a):
+            t = a[i]
+            if t.lower() == "-scale":
+                o.bsdf.TextureScale = (float(a[i + 1]), float(a[i + 2])); i += 3
+            elif t.lower() == "-off":
+                o.bsdf.TextureId = None; i += 1
+            elif t.lower() in ("-on", "-noupdate"):
+                i += 1
+            else:
+                if t not in self._texture_ids:
+                    if not os.path.exists(t):
+                        raise TclError(f"rttexture: failed to find image file at the path '{t}'")
+                    from PIL import Image
+                    self.textures.append(np.asarray(Image.open(t).convert("RGBA"), dtype=np.uint8))
+                    self._texture_ids[t] = len(self.textures) - 1
+                o.bsdf.TextureId = self._texture_ids[t]
+                i += 1
+        return ""
+
+    _d_vtexture = _d_rttexture
 
     def _d_rtdisplay(self, a):
         self._d_vdisplay(a)
@@ -863,12 +901,16 @@ class DrawSession(Interp):
                 continue
             pos, nrm, idx = o.shape.merged()
             s.add((pos, nrm, idx), o.location.astype(np.float32), o.bsdf)
+            uv = o.shape.merged_uv()
+            if uv is not None:
+                s.mesh_uvs[len(s.meshes) - 1] = uv
             w = pos.astype(np.float64) @ o.location[:, :3].T + o.location[:, 3]
             lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
         if not np.isfinite(lo).all():
             lo, hi = np.zeros(3), np.ones(3)
         s.params = self.params
         s.envmap = self.envmap
+        s.textures = list(self.textures)
         proj = self.proj / np.linalg.norm(self.proj)
         if self.eye is not None and self.at is not None:
             eye, at = self.eye, self.at

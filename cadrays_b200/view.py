@@ -88,6 +88,10 @@ class Graphic3d_BSDF:
     Absorption: list = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])  # rgb colour + coefficient
     FresnelCoat: Graphic3d_Fresnel = field(default_factory=lambda: Graphic3d_Fresnel.CreateConstant(0.0))
     FresnelBase: Graphic3d_Fresnel = field(default_factory=lambda: Graphic3d_Fresnel.CreateConstant(1.0))
+    # texture map of the aspect (SetTextureMap / SetTextureMapOn, AisMesh.cxx:343-345): index into the
+    # view's texture list or None, and the "rttexture -scale S T" factors
+    TextureId: Optional[int] = None
+    TextureScale: tuple = (1.0, 1.0)
 
     @staticmethod
     def CreateDiffuse(weight):
@@ -127,10 +131,11 @@ class Graphic3d_BSDF:
     def to_c(self) -> crt_bsdf:
         c = crt_bsdf()
         c.Kc[:] = self.Kc
-        c.Kd[:] = [*self.Kd, 0.0]
+        tex = 0.0 if self.TextureId is None else float(self.TextureId + 1)
+        c.Kd[:] = [*self.Kd, tex]
         c.Ks[:] = self.Ks
-        c.Kt[:] = [*self.Kt, 0.0]
-        c.Le[:] = [*self.Le, 0.0]
+        c.Kt[:] = [*self.Kt, float(self.TextureScale[0]) if tex else 0.0]
+        c.Le[:] = [*self.Le, float(self.TextureScale[1]) if tex else 0.0]
         c.FresnelCoat[:] = self.FresnelCoat.Serialize()
         c.FresnelBase[:] = self.FresnelBase.Serialize()
         c.Absorption[:] = self.Absorption
@@ -283,6 +288,20 @@ class V3d_View:
         for i, b in enumerate(bsdfs):
             arr[i] = b.to_c() if isinstance(b, Graphic3d_BSDF) else b
         check(self._lib.crt_materials_set(self._ctx, arr, len(bsdfs)))
+
+    def AddTexture(self, image: np.ndarray) -> int:
+        """Graphic3d_Texture2Dmanual: uint8 (h, w, 3|4), rows top-down as in the image file."""
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] not in (3, 4):
+            raise ValueError("texture must be (h, w, 3) or (h, w, 4) uint8")
+        if img.shape[2] == 3:
+            img = np.ascontiguousarray(np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], axis=2))
+        out = C.c_uint32()
+        check(self._lib.crt_texture_create(self._ctx, img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[1], img.shape[0], C.byref(out)))
+        return out.value
+
+    def ClearTextures(self):
+        check(self._lib.crt_textures_clear(self._ctx))
 
     def SetLights(self, lights: Sequence[crt_light]):
         arr = (crt_light * max(len(lights), 1))()

@@ -54,10 +54,10 @@ typedef struct crt_context crt_context;
  * Graphic3d_BSDF as CADRays fills it (src/Launcher/MaterialEditor.cxx:281-331,
  * src/ImportExport/ImportExport.cxx:155-231).  128 bytes, 8 x vec4.
  *   Kc  rgb = coat specular weight,   w = coat roughness
- *   Kd  rgb = base diffuse weight,    w unused (texture id in OCCT)
+ *   Kd  rgb = base diffuse weight,    w = base-colour texture: id + 1, 0 = none (texture id in OCCT)
  *   Ks  rgb = base specular weight,   w = base roughness
- *   Kt  rgb = specular transmission,  w unused
- *   Le  rgb = emitted radiance,       w unused
+ *   Kt  rgb = specular transmission,  w = texture S scale (0 = 1; "rttexture -scale S T")
+ *   Le  rgb = emitted radiance,       w = texture T scale (0 = 1)
  *   FresnelCoat / FresnelBase: Graphic3d_Fresnel::Serialize() encoding
  *       Schlick    ( r,  g,  b, .)  with r >= 0
  *       Constant   (-1,  ., f,  .)
@@ -179,6 +179,14 @@ int crt_scene_clear(crt_context* ctx);
 /* Graphic3d_MaterialAspect::SetBSDF + SetMaterial
  * (src/Launcher/MaterialEditor.cxx:331-337, src/ImportExport/Utils.cxx:83-93). */
 int crt_materials_set(crt_context* ctx, const crt_bsdf* bsdfs, uint32_t n);
+
+/* Graphic3d_AspectFillArea3d::SetTextureMap(Graphic3d_Texture2Dmanual) + SetTextureMapOn
+ * (src/ImportExport/AisMesh.cxx:343-345, src/ImportExport/ImportExportPlugin.cxx:737-746 "rttexture").
+ * RGBA8, rows top-down as in the image file; sampled bilinearly with repeat wrap at the hit's
+ * interpolated texel coordinates (SmoothUV); Kd *= rgb^2 * a, a < 1 mixes in transmission.
+ * A material refers to texture id through crt_bsdf.Kd[3] = id + 1. */
+int crt_texture_create(crt_context* ctx, const uint8_t* rgba8, uint32_t w, uint32_t h, uint32_t* out_texture_id);
+int crt_textures_clear(crt_context* ctx);
 
 /* V3d_Viewer::SetLightOn / DelLight / UpdateLights
  * (src/Launcher/LightSourcesEditor.cxx:404-412). */

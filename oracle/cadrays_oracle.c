@@ -194,6 +194,9 @@ struct orc_scene {
   /* lights in shader form: emission, w = cosMax | radius; xyz = to-light dir | pos */
   float*         lights; uint32_t n_lights;   /* 8 floats per light */
   float*         env;    uint32_t env_w, env_h;
+  /* base-colour textures (Graphic3d_Texture2Dmanual on the aspect, AisMesh.cxx:343-345): RGBA8 texels
+   * of all textures back to back (rows top-down as in the image file), table = offset, w, h per texture */
+  uint8_t*       tex_data; uint32_t* tex_table; uint32_t n_tex;
   crt_params     params;
   crt_camera     cam;
   v3             cam_u, cam_v, cam_w;
@@ -247,7 +250,8 @@ orc_scene* orc_scene_from_blob(const void* blob, size_t size)
 void orc_scene_free(orc_scene* s)
 {
   if (!s) return;
-  free(s->storage); free(s->inst_geom); free(s->mats); free(s->lights); free(s->env); free(s);
+  free(s->storage); free(s->inst_geom); free(s->mats); free(s->lights); free(s->env);
+  free(s->tex_data); free(s->tex_table); free(s);
 }
 
 void orc_set_materials(orc_scene* s, const crt_bsdf* m, uint32_t n)
@@ -301,6 +305,23 @@ void orc_set_envmap_rgb8(orc_scene* s, const uint8_t* rgb, uint32_t w, uint32_t 
   s->env = (float*)malloc(sizeof(float) * n);
   for (size_t i = 0; i < n; ++i) { float c = (float)rgb[i] * (1.0f / 255.0f); s->env[i] = c * c; }
   s->env_w = w; s->env_h = h;
+}
+
+/* Textures: n RGBA8 images concatenated in `texels`, sizes[2k], sizes[2k+1] = width, height. */
+void orc_set_textures(orc_scene* s, const uint8_t* texels, const uint32_t* sizes, uint32_t n)
+{
+  free(s->tex_data); free(s->tex_table);
+  s->tex_data = NULL; s->tex_table = NULL; s->n_tex = 0;
+  if (!n) return;
+  size_t total = 0;
+  s->tex_table = (uint32_t*)malloc(sizeof(uint32_t) * 3 * n);
+  for (uint32_t k = 0; k < n; ++k) {
+    s->tex_table[3 * k] = (uint32_t)total; s->tex_table[3 * k + 1] = sizes[2 * k]; s->tex_table[3 * k + 2] = sizes[2 * k + 1];
+    total += (size_t)sizes[2 * k] * sizes[2 * k + 1];
+  }
+  s->tex_data = (uint8_t*)malloc(4 * total);
+  memcpy(s->tex_data, texels, 4 * total);
+  s->n_tex = n;
 }
 
 void orc_set_params(orc_scene* s, const crt_params* p) { s->params = *p; }
@@ -841,6 +862,30 @@ static v3 from_local(v3 v, const frame_t* f)
 
 static float cone_pdf(float cos_max) { return 1.0f / (ORC_2PI - cos_max * ORC_2PI); }
 
+/* textureLod(sampler, st, 0) with GL_LINEAR / GL_REPEAT, t = 0 at the bottom row of the image.
+ * Returns rgba in [0,1]. */
+static void tex_lookup(const orc_scene* s, uint32_t tex, float u, float v, float out[4])
+{
+  const uint32_t off = s->tex_table[3 * tex];
+  const int w = (int)s->tex_table[3 * tex + 1], h = (int)s->tex_table[3 * tex + 2];
+  float fx = fmaf(u, (float)w, -0.5f);
+  float fy = fmaf(1.0f - v, (float)h, -0.5f);
+  float flx = floorf(fx), fly = floorf(fy);
+  float ax = fx - flx, ay = fy - fly;
+  int x0 = (int)flx, y0 = (int)fly;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = ((x0 % w) + w) % w; x1 = ((x1 % w) + w) % w;
+  y0 = ((y0 % h) + h) % h; y1 = ((y1 % h) + h) % h;
+  const uint8_t* t = s->tex_data + 4 * (size_t)off;
+  for (int c = 0; c < 4; ++c) {
+    float c00 = (float)t[4 * (y0 * w + x0) + c] * (1.0f / 255.0f), c10 = (float)t[4 * (y0 * w + x1) + c] * (1.0f / 255.0f);
+    float c01 = (float)t[4 * (y1 * w + x0) + c] * (1.0f / 255.0f), c11 = (float)t[4 * (y1 * w + x1) + c] * (1.0f / 255.0f);
+    float top = c00 * (1.0f - ax) + c10 * ax;
+    float bot = c01 * (1.0f - ax) + c11 * ax;
+    out[c] = top * (1.0f - ay) + bot * ay;
+  }
+}
+
 /* Latlong + bilinear fetch, SURVEY A.7 (Z-up, V3d_XposYnegZpos at AppViewer.cxx:610):
  * u = (atan2(d.y, d.x) + pi) / 2pi, v = acos(d.z) / pi, so +Z looks at the top
  * row (row 0) of the image.  Bilinear, wrap in u, clamp in v. */
@@ -971,6 +1016,25 @@ static v3 path_trace(const orc_scene* s, v3 org, v3 dir, uint32_t* rng, crt_stat
     const crt_bsdf* mat = mat_id < s->n_mats ? s->mats + mat_id : &k_default_bsdf;
     bsdf_t B = bsdf_load(mat);
     if (st) st->shaded_hits++;
+
+    /* base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV): Kd *= rgb^2 * a,
+     * alpha < 1 mixes in transmission.  Kd.w = texture index + 1 (0 = none), Kt.w / Le.w = S / T scale. */
+    if (mat->Kd[3] >= 1.0f && (uint32_t)mat->Kd[3] - 1u < s->n_tex) {
+      const float* uv0 = s->vert_uv + 2 * (voff + tr[0]);
+      const float* uv1 = s->vert_uv + 2 * (voff + tr[1]);
+      const float* uv2 = s->vert_uv + 2 * (voff + tr[2]);
+      float w0 = (1.0f - hit.u) - hit.v;
+      float tu = (uv1[0] * hit.u + uv2[0] * hit.v) + uv0[0] * w0;
+      float tv = (uv1[1] * hit.u + uv2[1] * hit.v) + uv0[1] * w0;
+      float ss = mat->Kt[3] != 0.0f ? mat->Kt[3] : 1.0f, ts = mat->Le[3] != 0.0f ? mat->Le[3] : 1.0f;
+      float tc[4];
+      tex_lookup(s, (uint32_t)mat->Kd[3] - 1u, tu * ss, tv * ts, tc);
+      B.Kd = vmul(B.Kd, vscale(V(tc[0] * tc[0], tc[1] * tc[1], tc[2] * tc[2]), tc[3]));
+      if (tc[3] != 1.0f) {
+        float ia = 1.0f - tc[3];
+        B.Kt = V(ia + tc[3] * B.Kt.x, ia + tc[3] * B.Kt.y, ia + tc[3] * B.Kt.z);
+      }
+    }
 
     v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), &frame);
 

@@ -35,6 +35,7 @@ void orc_set_materials(orc_scene* s, const crt_bsdf* m, uint32_t n);
 void orc_set_lights(orc_scene* s, const crt_light* l, uint32_t n);
 void orc_set_envmap_rgb32f(orc_scene* s, const float* rgb, uint32_t w, uint32_t h);
 void orc_set_envmap_rgb8(orc_scene* s, const uint8_t* rgb, uint32_t w, uint32_t h);
+void orc_set_textures(orc_scene* s, const uint8_t* rgba8_texels, const uint32_t* sizes_wh, uint32_t n);
 void orc_set_params(orc_scene* s, const crt_params* p);
 void orc_set_camera(orc_scene* s, const crt_camera* c);
 

@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         L.orc_set_lights.argtypes = [C.c_void_p, C.POINTER(crt_light), C.c_uint32]
         L.orc_set_envmap_rgb32f.argtypes = [C.c_void_p, _f, C.c_uint32, C.c_uint32]
         L.orc_set_envmap_rgb8.argtypes = [C.c_void_p, _u8, C.c_uint32, C.c_uint32]
+        L.orc_set_textures.argtypes = [C.c_void_p, _u8, C.POINTER(C.c_uint32), C.c_uint32]
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(crt_params)]
         L.orc_set_camera.argtypes = [C.c_void_p, C.POINTER(crt_camera)]
         L.orc_trace.argtypes = [C.c_void_p, _f, _f, _f, C.c_uint32, C.c_int, _i32, _i32, _f, _f, _f, C.POINTER(crt_stats)]
@@ -130,6 +131,18 @@ class OracleScene:
         else:
             a = np.ascontiguousarray(desc.envmap[..., :3], dtype=np.float32)
             self._L.orc_set_envmap_rgb32f(self._h, _fp(a), a.shape[1], a.shape[0])
+        texs = []
+        for t in getattr(desc, "textures", []):
+            t = np.ascontiguousarray(t, dtype=np.uint8)
+            if t.shape[2] == 3:
+                t = np.concatenate([t, np.full(t.shape[:2] + (1,), 255, np.uint8)], axis=2)
+            texs.append(np.ascontiguousarray(t))
+        if texs:
+            blob = np.concatenate([t.reshape(-1) for t in texs])
+            sizes = np.array([[t.shape[1], t.shape[0]] for t in texs], dtype=np.uint32).reshape(-1)
+            self._L.orc_set_textures(self._h, blob.ctypes.data_as(_u8), sizes.ctypes.data_as(C.POINTER(C.c_uint32)), len(texs))
+        else:
+            self._L.orc_set_textures(self._h, None, None, 0)
         p = desc.params.to_c()
         self._L.orc_set_params(self._h, C.byref(p))
         desc.camera.Aspect = desc.width / desc.height

@@ -340,3 +340,27 @@ def test_level3_converged_4096spp(product_lib, oracle_lib):
     assert rel.max() <= 1e-5 and float(np.sqrt(np.mean((g - o) ** 2))) <= 1e-6 * float(o.mean())
     assert np.array_equal(g, o)
     view.Remove()
+
+
+def test_textured_scene_parity(product_lib, oracle_lib):
+    """Base-colour textures (SetTextureMap on the aspect, AisMesh.cxx:343-345; SmoothUV): bit-equal to the oracle."""
+    from tests.test_oracle_cpu import _textured_cornell
+    g = np.random.default_rng(9)
+    tex = (g.random((16, 12, 4)) * 255).astype(np.uint8)
+    desc = _textured_cornell(tex, scale=(3.0, 1.5), res=96)
+    desc.textures.append((g.random((5, 7, 3)) * 255).astype(np.uint8))      # second texture, RGB, on the floor
+    pos = desc.meshes[4][0]
+    desc.mesh_uvs[4] = np.stack([pos[:, 0] * 2.0, pos[:, 1] * 2.0], 1).astype(np.float32)
+    desc.materials[4].TextureId = 1
+    view, orc = _pair(desc)
+    view.Redraw(6)
+    acc = orc.render(96, 96, 6)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc))
+    # removing the textures changes the image (they were really used)
+    desc.textures = []
+    desc.materials[2].TextureId = None
+    desc.materials[4].TextureId = None
+    desc.apply(view)
+    view.Redraw(6)
+    assert not np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc))
+    view.Remove()

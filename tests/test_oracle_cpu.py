@@ -316,3 +316,56 @@ def test_golden_fixtures(product_lib, oracle_lib):
     acc = o.render(meta["width"], meta["height"], meta["spp"])
     assert np.array_equal(acc, g["accum"])
     assert np.array_equal(o.display(acc), g["ldr"])
+
+
+def _textured_cornell(tex, scale=(1.0, 1.0), res=48):
+    d = scenes.cornell_box(res, res, depth=4, sphere_res=(12, 6))
+    d.textures = [tex]
+    pos = d.meshes[2][0]                                   # back wall: u = x, v = z
+    d.mesh_uvs[2] = np.stack([pos[:, 0], pos[:, 2]], 1).astype(np.float32)
+    d.materials[2].TextureId = 0
+    d.materials[2].TextureScale = scale
+    return d
+
+
+def test_base_colour_texture_semantics(product_lib, oracle_lib):
+    """USE_TEXTURES path: Kd *= rgb^2 * a (gamma-2 de-gamma), interpolated texel coordinates (SmoothUV),
+    t = 0 at the bottom row of the image, repeat wrap, -scale S T."""
+    # a constant texture is the same as scaling Kd by c^2
+    c = 128
+    tex = np.full((4, 4, 4), 255, np.uint8); tex[..., :3] = c
+    o = _oracle(_textured_cornell(tex))
+    img = o.hdr(o.render(48, 48, 16))
+    plain = scenes.cornell_box(48, 48, depth=4, sphere_res=(12, 6))
+    k = (c / 255.0) ** 2
+    plain.materials[2].Kd = [v * k for v in plain.materials[2].Kd]
+    o2 = _oracle(plain)
+    img2 = o2.hdr(o2.render(48, 48, 16))
+    assert np.allclose(img, img2, rtol=2e-3, atol=2e-3)
+    # orientation: t = 0 is the bottom row of the image file -> a texture whose TOP row is red puts the red band
+    # near the top of the wall, one whose BOTTOM row is red near the floor; -scale 2 2 repeats it
+    def red_rows(tex, scale=(1.0, 1.0)):
+        d = _textured_cornell(tex, scale=scale, res=64)
+        d.params.RaytracingDepth = 1                     # direct light at the first hit only
+        o = _oracle(d)
+        return o.hdr(o.render(64, 64, 48))[:, 20:44, 0].sum(axis=1)
+    top = np.zeros((8, 8, 4), np.uint8); top[..., 3] = 255; top[0, :, 0] = 255
+    bottom = np.zeros((8, 8, 4), np.uint8); bottom[..., 3] = 255; bottom[7, :, 0] = 255
+    diff = red_rows(top) - red_rows(bottom)              # > 0 where only `top` is red, < 0 where only `bottom` is
+    y = np.arange(64)
+    c_top = float((y * np.clip(diff, 0, None)).sum() / np.clip(diff, 0, None).sum())
+    c_bottom = float((y * np.clip(-diff, 0, None)).sum() / np.clip(-diff, 0, None).sum())
+    assert c_top > c_bottom + 15                         # image rows are bottom-up: larger = higher on the wall
+    diff2 = red_rows(top, scale=(2.0, 2.0)) - red_rows(bottom, scale=(2.0, 2.0))
+    bands = lambda v: int(np.sum((v[1:] > 0.25 * v.max()) & (v[:-1] <= 0.25 * v.max())))
+    assert bands(np.clip(diff, 0, None)) == 1 and bands(np.clip(diff2, 0, None)) == 2     # -scale 2 2 repeats the image
+    # alpha < 1 turns the remainder into transmission: a fully transparent texture makes the wall vanish
+    tex = np.zeros((2, 2, 4), np.uint8)
+    d3 = _textured_cornell(tex, res=32)
+    d3.params.RaytracingDepth = 3
+    d3.params.BackgroundColor = (0.0, 0.0, 0.0)
+    d3.envmap = np.full((2, 4, 3), 2.0, np.float32)
+    d3.params.UseEnvironmentMapBackground = True
+    o = _oracle(d3)
+    img = o.hdr(o.render(32, 32, 16))
+    assert img[12:20, 12:20].mean() > 1.5                 # the environment is seen through the wall

@@ -212,3 +212,26 @@ vlight add positional position 5 5 5 head 0 smoothness 0.2 intensity 40
     assert d.lights[0].is_point == 1 and d.lights[0].smoothness == pytest.approx(0.2)
     with pytest.raises(tcl.TclError):
         tcl.load_script(str(model), 8, 8).eval("rtmeshread /nonexistent.ply X")
+
+
+def test_rttexture_binds_a_texture_with_scale(tmp_path):
+    from PIL import Image
+    from cadrays_b200 import ply
+    img = (np.random.default_rng(3).random((6, 5, 3)) * 255).astype(np.uint8)
+    Image.fromarray(img).save(tmp_path / "wood.png")
+    pos, nrm, idx = scenes.uv_sphere(1.0, 8, 4)
+    uv = np.stack([pos[:, 0], pos[:, 1]], 1).astype(np.float32)
+    ply.write_ply(str(tmp_path / "m.ply"), pos, nrm, idx, uv=uv)
+    s = tcl.DrawSession(32, 32, root=str(tmp_path))
+    s.strict = True
+    s.eval('rtmeshread $Root/m.ply M\nrtdisplay M\nrttexture M "$Root/wood.png"\nrttexture M -scale 2 3\nbox b 1 1 1\nvdisplay b')
+    d = s.scene()
+    assert len(d.textures) == 1 and d.textures[0].shape == (6, 5, 4) and np.array_equal(d.textures[0][..., :3], img)
+    b = d.materials[d.instances[0][2]]
+    assert b.TextureId == 0 and b.TextureScale == (2.0, 3.0)
+    c = b.to_c()
+    assert c.Kd[3] == 1.0 and c.Kt[3] == 2.0 and c.Le[3] == 3.0
+    assert np.allclose(d.mesh_uvs[0], uv) and 1 not in d.mesh_uvs
+    assert d.materials[d.instances[1][2]].to_c().Kd[3] == 0.0
+    with pytest.raises(tcl.TclError):
+        s.eval("rttexture M /no/such/file.png")
