@@ -952,7 +952,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
         const uint32_t mat_id = (uint32_t)__float_as_int(m3.y);
         Bsdf B;
         v3 mat_le, absorp;
-        float absorp_k;
+        float absorp_k, kd_w = 0.0f, kt_w = 0.0f, le_w = 0.0f;   // texture id + 1, S scale, T scale
         if (mat_id < S.n_mats) {
           const float4* mp = S.mats + 8 * (size_t)mat_id;
           const float4 kc = __ldg(mp), kd = __ldg(mp + 1), ks = __ldg(mp + 2), kt = __ldg(mp + 3);
@@ -964,6 +964,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
           B.Fc = V(fc.x, fc.y, fc.z); B.Fb = V(fb.x, fb.y, fb.z);
           mat_le = V(le4.x, le4.y, le4.z);
           absorp = V(ab.x, ab.y, ab.z); absorp_k = ab.w;
+          kd_w = kd.w; kt_w = kt.w; le_w = le4.w;
         } else {   // default grey diffuse (same record as the oracle's k_default_bsdf)
           B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kd = V(0.8f, 0.8f, 0.8f); B.Ks = V(0, 0, 0); B.Ks_w = 0.0f;
           B.Kt = V(0, 0, 0); B.Fc = V(-1.0f, 0.0f, 0.0f); B.Fb = V(-1.0f, 0.0f, 1.0f);
@@ -972,15 +973,13 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
         if (COUNT) cnt.shaded_hits++;
 
         // base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV)
-        if (mat_id < S.n_mats) {
-          const float kd_w = __ldg(S.mats + 8 * (size_t)mat_id + 1).w;
+        {
           if (kd_w >= 1.0f && (uint32_t)kd_w - 1u < S.n_tex) {
             const float2* tu = S.tri_uv + 3 * (size_t)tri;
             const float2 uv0 = __ldg(tu), uv1 = __ldg(tu + 1), uv2 = __ldg(tu + 2);
             const float w0 = (1.0f - hh.y) - hh.z;
             const float su = (uv1.x * hh.y + uv2.x * hh.z) + uv0.x * w0;
             const float sv = (uv1.y * hh.y + uv2.y * hh.z) + uv0.y * w0;
-            const float kt_w = __ldg(S.mats + 8 * (size_t)mat_id + 3).w, le_w = __ldg(S.mats + 8 * (size_t)mat_id + 4).w;
             const float ss = kt_w != 0.0f ? kt_w : 1.0f, ts = le_w != 0.0f ? le_w : 1.0f;
             const float4 tc = tex_lookup(S, (uint32_t)kd_w - 1u, su * ss, sv * ts);
             B.Kd = vmul(B.Kd, vscale(V(tc.x * tc.x, tc.y * tc.y, tc.z * tc.z), tc.w));
