@@ -385,7 +385,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     }
     {
       SpanGuard g(c, F_SHADE);
-      k_shade<COUNT><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
+      if (c->ds.n_tex) k_shade<COUNT, true><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
+      else k_shade<COUNT, false><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
     }
     if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT);

@@ -11,7 +11,7 @@
 // from device memory, so a whole wave is enqueued without a host round trip.
 // Traversal kernels are persistent (grid = SM count x resident CTAs): each lane
 // pulls its next ray from a warp-local pool as soon as its ray finishes
-// (trace_persistent); shading kernels grid-stride with a grid that is a multiple
+// (trace_persistent, traversal stack in shared memory); shading kernels grid-stride with a grid that is a multiple
 // of the SM count.  One wave:
 //   k_generate -> k_extend(0) -> k_shade(0) -> [k_trace_dual(d) -> k_shade(d)]... -> k_connect -> k_resolve
 #pragma once
@@ -177,7 +177,27 @@ __device__ __forceinline__ v3 xf_vector(float4 r0, float4 r1, float4 r2, v3 p)
 // (measured: 5 of 32 lanes active per instruction, profiles/r01_*).
 constexpr int32_t kDone = -1;
 
-__device__ __forceinline__ int32_t stack_pop(const int32_t* stack, int& sp, Ray& r, v3 org, v3 dir)
+// Traversal stack storage.  Local memory (one private array per thread) costs up to 32 L1 wavefronts per
+// push/pop when the lanes of a warp sit at different depths; CRT_SMEM_STACK = D > 0 keeps D levels per
+// thread in shared memory laid out [level][thread] (bank = lane: always one wavefront).
+#ifndef CRT_SMEM_STACK
+#define CRT_SMEM_STACK 28
+#endif
+struct LocalStack {
+  int32_t* base;
+  __device__ __forceinline__ int32_t& operator[](int i) const { return base[i]; }
+};
+struct SharedStack {
+  int32_t* base;       // &smem[threadIdx.x]; levels 0 .. CRT_SMEM_STACK-1
+  int32_t* overflow;   // deeper levels spill to a private local array (rare: 2-level trees of depth > 28)
+  __device__ __forceinline__ int32_t& operator[](int i) const
+  {
+    return i < CRT_SMEM_STACK ? base[i * 128] : overflow[i - CRT_SMEM_STACK];
+  }
+};
+
+template <class Stack>
+__device__ __forceinline__ int32_t stack_pop(const Stack& stack, int& sp, Ray& r, v3 org, v3 dir)
 {
   if (sp == 0) return kDone;
   int32_t c = stack[--sp];
@@ -277,8 +297,11 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_CHUNK
 #define CRT_CHUNK 64
 #endif
+#ifndef CRT_INNER_EXIT
+#define CRT_INNER_EXIT 1
+#endif
 #ifndef CRT_TRACE_MIN_BLOCKS
-#define CRT_TRACE_MIN_BLOCKS 1
+#define CRT_TRACE_MIN_BLOCKS 7
 #endif
 constexpr uint32_t kChunk = CRT_CHUNK;
 
@@ -300,7 +323,14 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   r.setup(org, dir);
   Hit hit;
   hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
-  int32_t stack[kStackSize];
+#if CRT_SMEM_STACK > 0
+  __shared__ int32_t s_stack[CRT_SMEM_STACK * 128];
+  int32_t stack_overflow[kStackSize - CRT_SMEM_STACK];
+  const SharedStack stack{ s_stack + threadIdx.x, stack_overflow };
+#else
+  int32_t stack_mem[kStackSize];
+  const LocalStack stack{ stack_mem };
+#endif
   int sp = 0;
   int32_t inst = -1;
   for (;;) {
@@ -334,10 +364,13 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
       }
       pool_next += min(avail, (uint32_t)__popc(m));
     }
-    if (drained && __all_sync(FULL, !has_ray)) break;
+    const unsigned live = __ballot_sync(FULL, has_ray);
+    if (drained && live == 0) break;
+    const int n_live = __popc(live);
 
-    // ---- inner nodes.  (A variant that left this loop once fewer than N lanes were still walking
-    // inner nodes was measured: the two extra votes per iteration cost more than the regained lanes.)
+    // ---- inner nodes.  CRT_INNER_EXIT = N > 1: lanes leave the loop once fewer than N lanes are still
+    // walking inner nodes while another lane of the warp waits for its leaf / instance step (the
+    // simulator tools/simt_model.py predicts fewer issue slots per ray for N around 12).
     while (cur >= 0) {
       {
         if (COUNT) { if (any_ray) cnt.n_inner_any++; else cnt.n_inner++; }
@@ -365,6 +398,12 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
           cur = stack_pop(stack, sp, r, org, dir);
         }
       }
+#if CRT_INNER_EXIT > 1
+      {
+        const int walking = __popc(__activemask());
+        if (walking < CRT_INNER_EXIT && walking < n_live) break;
+      }
+#endif
     }
     // ---- one leaf / instance step
     if (cur < 0 && cur != kDone) {
@@ -886,7 +925,7 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 #ifndef CRT_SHADE_MIN_BLOCKS
 #define CRT_SHADE_MIN_BLOCKS 8
 #endif
-template <bool COUNT>
+template <bool COUNT, bool TEX>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
 {
@@ -973,7 +1012,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
         if (COUNT) cnt.shaded_hits++;
 
         // base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV)
-        {
+        if (TEX) {   // instantiated only for scenes that have textures
           if (kd_w >= 1.0f && (uint32_t)kd_w - 1u < S.n_tex) {
             const float2* tu = S.tri_uv + 3 * (size_t)tri;
             const float2 uv0 = __ldg(tu), uv1 = __ldg(tu + 1), uv2 = __ldg(tu + 2);

@@ -432,3 +432,24 @@ def random_rays(n: int, lo, hi, seed: int = 7):
     d = g.normal(size=(n, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return org, d.astype(np.float32)
+
+
+def deep_tree_scene(n=700, base=1.1, n_inst=100, inst_base=1.15, width=64, height=48) -> SceneDesc:
+    """Degenerate test scene: exponentially spaced triangles / instances make the SAH builder peel a few
+    primitives per level, so the two-level tree is deeper (> 28 levels together) than the traversal's
+    shared-memory stack and exercises its local-memory overflow."""
+    d = SceneDesc("deep", width=width, height=height)
+    k = np.arange(n)
+    x = base ** k * 1e-3
+    s = x * 0.04
+    z = np.zeros(n)
+    pos = np.stack([np.stack([x - s, -s, z], 1), np.stack([x + s, -s, z], 1), np.stack([x, s, z], 1)], 1).reshape(-1, 3)
+    d.meshes.append((pos.astype(np.float32), np.tile(np.array([[0, 0, 1]], np.float32), (3 * n, 1)),
+                     np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)))
+    d.materials.append(Graphic3d_BSDF(Kd=[0.7, 0.7, 0.7]))
+    for j in range(n_inst):
+        d.instances.append((0, trsf((0.0, 1e-2 * inst_base ** j, 0.0)), 0))
+    d.lights = [make_light(False, (0.1, 0.2, -1.0), intensity=3.0, smoothness=0.1)]
+    d.camera = look_at((20.0, 20.0, 120.0), (20.0, 20.0, 0.0), up=(0, 1, 0), fovy=40.0)
+    d.params = Graphic3d_RenderingParams(RaytracingDepth=3)
+    return d

@@ -441,6 +441,11 @@ static inline v3 xf_vector(const float* m, v3 p)
            fmaf(m[10], p.z, fmaf(m[9], p.y, m[8] * p.x)));
 }
 
+/* optional per-ray event recorder (analysis tooling: feeds tools/simt_model.py) */
+static __thread uint8_t* g_ev = NULL;
+static __thread int g_ev_n = 0, g_ev_cap = 0;
+#define ORC_EVENT(code) do { if (g_ev && g_ev_n < g_ev_cap) g_ev[g_ev_n++] = (uint8_t)(code); } while (0)
+
 /* SceneNearestHit / SceneAnyHit, SURVEY A.3. */
 static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit, hit_t* hit,
                     crt_stats* st)
@@ -460,7 +465,7 @@ static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit,
   for (;;) {
     const int32_t* info = s->node_info + 4 * node;
     if (info[0] == 0) {                                   /* inner node */
-      ++n_inner;
+      ++n_inner; ORC_EVENT(1);
       int l = node_off + info[1], r = node_off + info[2];
       float tl, tr;
       int hl = slab(&cur, s->node_min + 3 * l, s->node_max + 3 * l, hit->t, &tl);
@@ -475,7 +480,7 @@ static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit,
       if (hl) { node = l; continue; }
       if (hr) { node = r; continue; }
     } else if (info[0] < 0) {                             /* bottom-level leaf */
-      ++n_leaf;
+      ++n_leaf; ORC_EVENT(3 + (info[2] - info[1] + 1));
       for (int i = info[1]; i <= info[2]; ++i) {
         const int32_t* tr = s->tris + 4 * (tri_off + i);
         ++n_tri;
@@ -488,7 +493,7 @@ static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit,
         }
       }
     } else {                                              /* top-level leaf: enter instance */
-      ++n_switch;
+      ++n_switch; ORC_EVENT(2);
       inst = info[0] - 1; node_off = info[1]; vert_off = info[2]; tri_off = info[3];
       const float* m = s->inst_inv + 16 * inst;
       ray_setup(&cur, xf_point(m, world.o), xf_vector(m, world.d));
@@ -527,6 +532,20 @@ void orc_trace(const orc_scene* s, const float* org, const float* dir, const flo
     if (t) t[i] = h.t;
     if (u) u[i] = h.u;
     if (v) v[i] = h.v;
+  }
+}
+
+/* Event strings of the traversal of each ray: 1 = inner node, 2 = instance switch, 3+k = leaf with k
+ * triangles.  events: n x cap bytes, lens: n ints.  Analysis tooling only. */
+void orc_trace_events(const orc_scene* s, const float* org, const float* dir, const float* tmax, uint32_t n,
+                      int any_hit, uint8_t* events, int cap, int32_t* lens)
+{
+  for (uint32_t i = 0; i < n; ++i) {
+    hit_t h;
+    g_ev = events + (size_t)i * cap; g_ev_n = 0; g_ev_cap = cap;
+    traverse(s, ld3(org, i), ld3(dir, i), tmax ? tmax[i] : ORC_MAXFLOAT, any_hit, &h, NULL);
+    lens[i] = g_ev_n;
+    g_ev = NULL;
   }
 }
 

@@ -50,6 +50,9 @@ void orc_trace_brute(const orc_scene* s, const float* org, const float* dir, con
                      uint32_t n, int any_hit,
                      int32_t* prim, int32_t* inst, float* t, float* u, float* v);
 
+void orc_trace_events(const orc_scene* s, const float* org, const float* dir, const float* tmax, uint32_t n,
+                      int any_hit, uint8_t* events, int cap, int32_t* lens);
+
 /* PathTrace + accumulation: adds samples
  * [first_sample, first_sample + n_samples) of every pixel to accum4
  * (float4 per pixel, rgb = radiance sum, a = sample count; bottom-up rows).

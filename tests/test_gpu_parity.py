@@ -364,3 +364,47 @@ def test_textured_scene_parity(product_lib, oracle_lib):
     view.Redraw(6)
     assert not np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc))
     view.Remove()
+
+
+def test_deep_tree_exceeds_the_shared_stack(product_lib, oracle_lib):
+    """Two-level tree deeper than the 28 shared-memory stack levels: the overflow path gives the same hits."""
+    import struct
+    desc = scenes.deep_tree_scene()
+    view, orc = _pair(desc)
+    blob = view.ExportBVH()
+    h = struct.unpack_from("<8I", blob, 0)
+    info = np.frombuffer(blob, np.int32, 4 * h[2], 64).reshape(-1, 4)
+
+    def depth(root, off):
+        best, st = 0, [(root, 0)]
+        while st:
+            k, dp = st.pop()
+            best = max(best, dp)
+            if info[k][0] == 0:
+                st += [(off + info[k][1], dp + 1), (off + info[k][2], dp + 1)]
+        return best
+    total = depth(0, 0) + 1 + max(depth(r[1], r[1]) for r in info[:h[6]] if r[0] > 0)
+    assert total > 28, total
+    g = np.random.default_rng(2)
+    n = 20000
+    # rays skimming along the row of triangles / the column of instances: both children hit at every level
+    org = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+    org[:, 0] = -1.0; org[:, 1] = g.uniform(0.0, 30.0, n); org[:, 2] = g.uniform(-1e-3, 1e-3, n)
+    d[:, 0] = 1.0; d[:, 1] = g.normal(0, 1e-3, n); d[:, 2] = g.normal(0, 1e-5, n)
+    half = n // 2
+    org[half:, 0] = g.uniform(0.0, 5.0, n - half); org[half:, 1] = -1.0
+    d[half:, 0] = g.normal(0, 1e-3, n - half); d[half:, 1] = 1.0
+    view.EnableStats(True); view.ResetStats()
+    a = view.Trace(org, d)
+    gs = view.Stats()
+    view.EnableStats(False)
+    b = orc.trace(org, d, stats=True)
+    for x, y in zip(a, b[:5]):
+        assert np.array_equal(x, y)
+    assert (a[0] >= 0).sum() > 100
+    for k in ("n_inner", "n_leaf", "n_tri", "n_switch"):
+        assert gs[k] == b[5][k], k
+    assert gs["n_inner"] / n > 60                      # these rays really walk deep
+    view.Redraw(2)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(orc.render(desc.width, desc.height, 2)))
+    view.Remove()

@@ -1,0 +1,192 @@
+"""Offline SIMT cost model of traversal control-flow strategies (analysis tooling, CPU only).
+
+Takes real per-ray traversal event strings from the oracle (1 = inner node, 2 = instance switch,
+3+k = leaf with k triangles) for a scene, groups rays into 32-lane warps with per-lane refill, and
+counts warp-level instruction issue for several loop structures.  Instruction costs per step come
+from the SASS of the current kernels.  Used to decide what is worth building before spending GPU time.
+
+  python tools/simt_model.py [--rays 65536] [--scene assembly]
+"""
+import argparse
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+C_N, C_S, C_L0, C_T, C_R = 50, 100, 15, 45, 40
+
+
+def get_events(desc, org, d, tmax=None, any_hit=False, cap=512):
+    from cadrays_b200.view import V3d_View
+    from oracle import oracle_ffi
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    o = oracle_ffi.OracleScene(v.ExportBVH())
+    L = oracle_ffi.lib()
+    L.orc_trace_events.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32,
+                                   C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int32)]
+    n = org.shape[0]
+    ev = np.zeros((n, cap), np.uint8)
+    lens = np.zeros(n, np.int32)
+    fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+    L.orc_trace_events(o._h, fp(org), fp(d), fp(tmax), n, int(any_hit), ev.ctypes.data_as(C.POINTER(C.c_uint8)), cap,
+                       lens.ctypes.data_as(C.POINTER(C.c_int32)))
+    prim, inst, t, u, vv = o.trace(org, d, tmax, any_hit=any_hit)
+    return [ev[i, :lens[i]].tolist() for i in range(n)], prim, t
+
+
+def secondary_rays(desc, n, seed=1):
+    """Camera rays -> hit points -> random directions in the hemisphere facing the camera (diffuse-bounce proxy)."""
+    from cadrays_b200.view import V3d_View
+    from oracle import oracle_ffi
+    g = np.random.default_rng(seed)
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    o = oracle_ffi.OracleScene(v.ExportBVH())
+    o.configure(desc)
+    L = oracle_ffi.lib()
+    w, h = desc.width, desc.height
+    side = int(np.sqrt(n * 2.5))
+    xs = (np.arange(side) + 0.5) / side
+    org = np.zeros((side * side, 3), np.float32); d = np.zeros_like(org)
+    oo = (C.c_float * 3)(); dd = (C.c_float * 3)()
+    k = 0
+    # tile order 8x4 like the kernel: iterate tiles then lanes
+    for ty in range(0, side, 4):
+        for tx in range(0, side, 8):
+            for ly in range(4):
+                for lx in range(8):
+                    x, y = tx + lx, ty + ly
+                    if x >= side or y >= side:
+                        continue
+                    L.orc_camera_ray(o._h, float(xs[x]), float(xs[y]), 0.0, 0.0, oo, dd)
+                    org[k] = oo[:]; d[k] = dd[:]; k += 1
+    org, d = org[:k], d[:k]
+    prim, inst, t, u, vv = o.trace(org, d)
+    hit = prim >= 0
+    p = org[hit] + d[hit] * t[hit, None]
+    r = g.normal(size=p.shape); r /= np.linalg.norm(r, axis=1, keepdims=True)
+    flip = np.sum(r * (-d[hit]), axis=1) < 0
+    r[flip] = -r[flip]
+    eps = 1e-3
+    sec_o = (p + r * eps - d[hit] * eps).astype(np.float32)
+    return (org, d), (sec_o[:n], r[:n].astype(np.float32))
+
+
+def simulate(events, strategy, threshold=1):
+    """Returns (warp instruction issues, useful lane instructions)."""
+    n = len(events)
+    pos_ray = 0
+    total_issue = 0
+    useful = 0
+    for e in events:
+        for c in e:
+            useful += C_N if c == 1 else (C_S if c == 2 else C_L0 + C_T * (c - 3))
+    # one persistent warp per 32 * 64 rays is enough to see the steady state; process warps sequentially
+    chunk = 32 * 64
+    for base in range(0, n, chunk):
+        pool = list(range(base, min(base + chunk, n)))
+        pool.reverse()
+        lanes = [None] * 32          # (event list, index)
+        while True:
+            # refill
+            need = [i for i in range(32) if lanes[i] is None]
+            if need and pool:
+                total_issue += C_R
+                for i in need:
+                    if pool:
+                        lanes[i] = [events[pool.pop()], 0]
+            for i in range(32):
+                if lanes[i] is not None and lanes[i][1] >= len(lanes[i][0]):
+                    lanes[i] = None
+            if all(l is None for l in lanes):
+                if not pool:
+                    break
+                continue
+            nxt = lambda l: l[0][l[1]] if l is not None and l[1] < len(l[0]) else 0
+            if strategy in ("while-while", "inloop-switch"):
+                # inner loop
+                while True:
+                    kinds = [nxt(l) for l in lanes]
+                    n_inner = sum(1 for k in kinds if k == 1)
+                    n_sw = sum(1 for k in kinds if k == 2) if strategy == "inloop-switch" else 0
+                    if n_inner + n_sw == 0:
+                        break
+                    if n_inner < threshold and any(k > (2 if strategy == "inloop-switch" else 1) for k in kinds):
+                        break
+                    total_issue += (C_N if n_inner else 0) + (C_S if n_sw else 0) + (4 if threshold > 1 else 0)
+                    for l, k in zip(lanes, kinds):
+                        if k == 1 or (k == 2 and strategy == "inloop-switch"):
+                            l[1] += 1
+                kinds = [nxt(l) for l in lanes]
+                if any(k == 2 for k in kinds):
+                    total_issue += C_S
+                ks = [k - 3 for k in kinds if k >= 3]
+                if ks:
+                    total_issue += C_L0 + C_T * max(ks)
+                for l, k in zip(lanes, kinds):
+                    if k >= 2:
+                        l[1] += 1
+            elif strategy == "if-if":
+                kinds = [nxt(l) for l in lanes]
+                if any(k == 1 for k in kinds):
+                    total_issue += C_N
+                if any(k == 2 for k in kinds):
+                    total_issue += C_S
+                ks = [k - 3 for k in kinds if k >= 3]
+                if ks:
+                    total_issue += C_L0 + C_T * max(ks)
+                for l, k in zip(lanes, kinds):
+                    if k:
+                        l[1] += 1
+            elif strategy == "tri-step":
+                # leaves are processed one triangle per iteration, inside the same loop as inner nodes
+                kinds = [nxt(l) for l in lanes]
+                if any(k == 1 for k in kinds):
+                    total_issue += C_N
+                if any(k == 2 for k in kinds):
+                    total_issue += C_S
+                if any(k >= 3 for k in kinds):
+                    total_issue += C_T + 5
+                for l, k in zip(lanes, kinds):
+                    if k in (1, 2) or k == 3 or k == 4:
+                        l[1] += 1
+                    elif k > 4:
+                        l[0] = list(l[0]); l[0][l[1]] = k - 1
+            for i in range(32):
+                if lanes[i] is not None and lanes[i][1] >= len(lanes[i][0]):
+                    lanes[i] = None
+    return total_issue, useful
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=32768)
+    ap.add_argument("--scene", default="assembly")
+    args = ap.parse_args()
+    from cadrays_b200 import scenes
+    desc = scenes.assembly(width=512, height=512) if args.scene == "assembly" else scenes.cornell_box(512, 512)
+    (po, pd), (so, sd) = secondary_rays(desc, args.rays)
+    for name, (o, d) in (("primary (coherent)", (po[:args.rays], pd[:args.rays])), ("secondary (incoherent)", (so, sd))):
+        ev, prim, t = get_events(desc, o, d)
+        steps = np.array([len(e) for e in ev])
+        print(f"== {name}: {len(ev)} rays, mean steps {steps.mean():.1f}, max {steps.max()}, hit {np.mean(prim >= 0):.2f}")
+        for strat, thr in (("while-while", 1), ("while-while", 12), ("while-while", 20), ("inloop-switch", 1), ("if-if", 1), ("tri-step", 1)):
+            issue, useful = simulate(ev, strat, thr)
+            print(f"   {strat:14s} thr={thr:2d}: warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
+        # sorted variant: group rays by origin cell + direction octant before forming warps
+        lo, hi = o.min(0), o.max(0)
+        cell = np.clip(((o - lo) / np.maximum(hi - lo, 1e-9) * 16).astype(int), 0, 15)
+        key = (((d[:, 0] < 0) * 4 + (d[:, 1] < 0) * 2 + (d[:, 2] < 0)) << 12) | (cell[:, 0] << 8) | (cell[:, 1] << 4) | cell[:, 2]
+        order = np.argsort(key, kind="stable")
+        ev_sorted = [ev[i] for i in order]
+        issue, useful = simulate(ev_sorted, "while-while", 1)
+        print(f"   {'sorted + w-w':14s}        : warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
+
+
+if __name__ == "__main__":
+    main()
