@@ -11,7 +11,7 @@
 // from device memory, so a whole wave is enqueued without a host round trip.
 // Traversal kernels are persistent (grid = SM count x resident CTAs): each lane
 // pulls its next ray from a warp-local pool as soon as its ray finishes
-// (trace_persistent, traversal stack in shared memory); shading kernels grid-stride with a grid that is a multiple
+// (trace_persistent); shading kernels grid-stride with a grid that is a multiple
 // of the SM count.  One wave:
 //   k_generate -> k_extend(0) -> k_shade(0) -> [k_trace_dual(d) -> k_shade(d)]... -> k_connect -> k_resolve
 #pragma once
@@ -181,7 +181,7 @@ constexpr int32_t kDone = -1;
 // push/pop when the lanes of a warp sit at different depths; CRT_SMEM_STACK = D > 0 keeps D levels per
 // thread in shared memory laid out [level][thread] (bank = lane: always one wavefront).
 #ifndef CRT_SMEM_STACK
-#define CRT_SMEM_STACK 28
+#define CRT_SMEM_STACK 0
 #endif
 struct LocalStack {
   int32_t* base;
@@ -301,7 +301,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #define CRT_INNER_EXIT 1
 #endif
 #ifndef CRT_TRACE_MIN_BLOCKS
-#define CRT_TRACE_MIN_BLOCKS 7
+#define CRT_TRACE_MIN_BLOCKS 1
 #endif
 constexpr uint32_t kChunk = CRT_CHUNK;
 

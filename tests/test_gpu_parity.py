@@ -366,8 +366,8 @@ def test_textured_scene_parity(product_lib, oracle_lib):
     view.Remove()
 
 
-def test_deep_tree_exceeds_the_shared_stack(product_lib, oracle_lib):
-    """Two-level tree deeper than the 28 shared-memory stack levels: the overflow path gives the same hits."""
+def test_deep_tree(product_lib, oracle_lib):
+    """Two-level tree of more than 28 levels (degenerate SAH splits): deep stacks give the same hits and counters."""
     import struct
     desc = scenes.deep_tree_scene()
     view, orc = _pair(desc)
