@@ -30,6 +30,9 @@ METRIC = "path-traced Msamples/s (1080p, depth 8)"
 UNIT = "Msamples/s"
 
 
+_OUT = sys.stdout
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,7 +194,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU oracle port (OpenMP over pixel rows); the OCCT/llvmpipe reference binary is not runnable here",
     }
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
 
 
 def run_ours(args):
@@ -338,7 +341,7 @@ def run_ours(args):
             blob = view.ExportBVH()
             v, dtc, sample = cpu_leg(args, desc, blob, os.cpu_count() or 1, 3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     view.Remove()
     if world > 1:
         dist.barrier()
@@ -347,6 +350,12 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout must carry exactly ONE JSON line.  Native libraries (NCCL's version banner, for one) print to
+    # file descriptor 1 directly, so route fd 1 to stderr for the whole run and keep the real stdout for us.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
