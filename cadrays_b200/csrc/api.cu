@@ -88,6 +88,7 @@ struct crt_context {
   // device scene
   DevBuf<float4> d_arena, d_mats, d_lights, d_env;
   DevBuf<float2> d_tri_uv;
+  DevBuf<float4> d_top_cache;
   DevBuf<uchar4> d_tex;
   DevBuf<uint32_t> d_tex_table;
   DeviceScene ds{};
@@ -260,6 +261,17 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
   if (!L.tri_uv.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_uv.p, L.tri_uv.data(), L.tri_uv.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CRT_CUDA(cudaStreamSynchronize(c->stream));
   c->ds.tri_uv = c->d_tri_uv.p;
+  {
+    // padded copy of the first top-level nodes (breadth-first = top of the tree) for shared-memory staging
+    const uint32_t n_cache = std::min<uint32_t>(L.n_top_inner, 1024u);
+    std::vector<f4> cache((size_t)5 * std::max<uint32_t>(n_cache, 1), f4{ 0, 0, 0, 0 });
+    for (uint32_t k = 0; k < n_cache; ++k)
+      for (int q = 0; q < 4; ++q) cache[5 * (size_t)k + q] = L.nodes[4 * (size_t)k + q];
+    CRT_CUDA(c->d_top_cache.ensure(cache.size()));
+    CRT_CUDA(cudaMemcpy(c->d_top_cache.p, cache.data(), cache.size() * 16, cudaMemcpyHostToDevice));
+    c->ds.top_cache = c->d_top_cache.p;
+    c->ds.n_top_cache = n_cache;
+  }
   c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
@@ -531,7 +543,7 @@ void crt_destroy(crt_context* c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   collect_spans(c);
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-  c->d_arena.release(); c->d_tri_uv.release(); c->d_tex.release(); c->d_tex_table.release();
+  c->d_arena.release(); c->d_top_cache.release(); c->d_tri_uv.release(); c->d_tex.release(); c->d_tex_table.release();
   c->d_mats.release(); c->d_lights.release(); c->d_env.release();
   c->ray_o.release(); c->ray_d.release(); c->thr.release(); c->rad.release(); c->hit.release();
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();

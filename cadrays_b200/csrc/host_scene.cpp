@@ -403,41 +403,66 @@ struct Converter {
     return self;
   }
 
-  int32_t top(int32_t node_abs, int depth)
+  // instance leaf of the top tree: converts (once per mesh) the bottom tree it points to
+  int32_t top_leaf(const int32_t* info)
   {
-    if (!ok) return kRefNone;
-    if (!node_ok(node_abs) || depth > 64) { err = "blob: top tree malformed"; ok = false; return kRefNone; }
-    out.max_depth_top = std::max(out.max_depth_top, depth);
-    const int32_t* info = v.node_info + 4 * (size_t)node_abs;
-    if (info[0] > 0) {
-      const int32_t k = info[0] - 1;
-      if (k >= (int32_t)v.hdr.n_inst) { err = "blob: instance index"; ok = false; return kRefNone; }
-      int32_t ref;
-      auto it = mesh_root_ref.find(info[1]);
-      if (it == mesh_root_ref.end()) {
-        cur_depth_max = 0;
-        ref = bottom(info[1], info[1], info[3], 0);
-        mesh_root_ref[info[1]] = ref;
-        out.max_depth_bottom = std::max(out.max_depth_bottom, cur_depth_max);
-      } else {
-        ref = it->second;
-      }
-      f4* ir = &out.inst[4 * (size_t)k];
-      ir[3].x = bits(ref);
-      return (int32_t)(kRefLeafBit | kRefInstBit | (uint32_t)k);
+    const int32_t k = info[0] - 1;
+    if (k >= (int32_t)v.hdr.n_inst) { err = "blob: instance index"; ok = false; return kRefNone; }
+    int32_t ref;
+    auto it = mesh_root_ref.find(info[1]);
+    if (it == mesh_root_ref.end()) {
+      cur_depth_max = 0;
+      ref = bottom(info[1], info[1], info[3], 0);
+      mesh_root_ref[info[1]] = ref;
+      out.max_depth_bottom = std::max(out.max_depth_bottom, cur_depth_max);
+    } else {
+      ref = it->second;
     }
-    if (info[0] != 0) { err = "blob: bottom leaf inside the top tree"; ok = false; return kRefNone; }
-    const int32_t self = (int32_t)(out.nodes.size() / 4);
-    out.nodes.resize(out.nodes.size() + 4, f4{ 0, 0, 0, 0 });
-    const int32_t l = info[1], r = info[2];
-    if (!node_ok(l) || !node_ok(r)) { err = "blob: child index"; ok = false; return kRefNone; }
-    const int32_t rl = top(l, depth + 1);
-    const int32_t rr = top(r, depth + 1);
-    f4* nd = &out.nodes[4 * (size_t)self];
-    set_box(nd, 0, v.node_min + 3 * (size_t)l, v.node_max + 3 * (size_t)l);
-    set_box(nd, 1, v.node_min + 3 * (size_t)r, v.node_max + 3 * (size_t)r);
-    nd[3].x = bits(rl); nd[3].y = bits(rr);
-    return self;
+    f4* ir = &out.inst[4 * (size_t)k];
+    ir[3].x = bits(ref);
+    return (int32_t)(kRefLeafBit | kRefInstBit | (uint32_t)k);
+  }
+
+  // Top-level tree in breadth-first order: device nodes 0 .. n_top_inner-1 are the top tree level by
+  // level, so "the first K nodes" is the top of the tree (what the kernels may stage in shared memory).
+  int32_t top(int32_t root_abs)
+  {
+    if (!node_ok(root_abs)) { err = "blob: top tree malformed"; ok = false; return kRefNone; }
+    if (v.node_info[4 * (size_t)root_abs] > 0) return top_leaf(v.node_info + 4 * (size_t)root_abs);
+    std::vector<std::pair<int32_t, int>> order;          // (blob node, depth) of inner nodes, BFS
+    std::unordered_map<int32_t, int32_t> index;
+    order.emplace_back(root_abs, 0);
+    index[root_abs] = 0;
+    for (size_t q = 0; q < order.size() && ok; ++q) {
+      const int32_t n = order[q].first;
+      const int depth = order[q].second;
+      out.max_depth_top = std::max(out.max_depth_top, depth + 1);
+      const int32_t* info = v.node_info + 4 * (size_t)n;
+      for (int c = 1; c <= 2; ++c) {
+        const int32_t ch = info[c];
+        if (!node_ok(ch) || depth > 64 || order.size() > (size_t)v.hdr.n_nodes) { err = "blob: top tree malformed"; ok = false; break; }
+        const int32_t ci = v.node_info[4 * (size_t)ch];
+        if (ci == 0) { index[ch] = (int32_t)order.size(); order.emplace_back(ch, depth + 1); }
+        else if (ci < 0) { err = "blob: bottom leaf inside the top tree"; ok = false; break; }
+      }
+    }
+    if (!ok) return kRefNone;
+    out.n_top_inner = (uint32_t)order.size();
+    out.nodes.resize(4 * order.size(), f4{ 0, 0, 0, 0 });
+    for (size_t q = 0; q < order.size() && ok; ++q) {
+      const int32_t* info = v.node_info + 4 * (size_t)order[q].first;
+      int32_t refs[2];
+      for (int c = 0; c < 2; ++c) {
+        const int32_t ch = info[1 + c];
+        const int32_t* ci = v.node_info + 4 * (size_t)ch;
+        refs[c] = ci[0] == 0 ? index[ch] : top_leaf(ci);
+      }
+      f4* nd = &out.nodes[4 * q];       // re-fetch: bottom() may have grown the vector
+      set_box(nd, 0, v.node_min + 3 * (size_t)info[1], v.node_max + 3 * (size_t)info[1]);
+      set_box(nd, 1, v.node_min + 3 * (size_t)info[2], v.node_max + 3 * (size_t)info[2]);
+      nd[3].x = bits(refs[0]); nd[3].y = bits(refs[1]);
+    }
+    return 0;
   }
 };
 
@@ -496,7 +521,7 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
     out.inst[4 * k + 3] = f4{ Converter::bits(kRefNone), Converter::bits(v.inst_meta[4 * k]), 0.0f, 0.0f };
   }
   Converter c{ v, out, err };
-  out.top_root = c.top(0, 0);
+  out.top_root = c.top(0);
   return c.ok;
 }
 

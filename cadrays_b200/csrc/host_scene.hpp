@@ -100,6 +100,7 @@ struct DeviceLayout {
   std::vector<f4> inst;
   int32_t top_root = kRefNone;
   uint32_t n_tris = 0, n_inst = 0;
+  uint32_t n_top_inner = 0;    // nodes[0 .. n_top_inner) = top-level tree in breadth-first order
   int max_depth_top = 0, max_depth_bottom = 0;
 };
 

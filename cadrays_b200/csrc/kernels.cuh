@@ -39,6 +39,10 @@ struct DeviceScene {
   int32_t top_root;
   uint32_t n_mats, n_lights, env_w, env_h;
   float scene_eps;
+  // top of the top-level tree (first nodes in breadth-first order), 80-byte stride (64 B node + 16 B pad
+  // so that scattered shared-memory reads spread over the banks); staged per CTA by one TMA bulk copy
+  const float4* __restrict__ top_cache;
+  uint32_t n_top_cache;
 };
 
 struct DeviceParams {
@@ -300,6 +304,9 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_INNER_EXIT
 #define CRT_INNER_EXIT 1
 #endif
+#ifndef CRT_SMEM_TOP
+#define CRT_SMEM_TOP 0
+#endif
 #ifndef CRT_TRACE_MIN_BLOCKS
 #define CRT_TRACE_MIN_BLOCKS 1
 #endif
@@ -330,6 +337,33 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
 #else
   int32_t stack_mem[kStackSize];
   const LocalStack stack{ stack_mem };
+#endif
+#if CRT_SMEM_TOP > 0
+  // stage the top of the top-level tree in shared memory: one cp.async.bulk (TMA, UBLKCP) per CTA,
+  // completion through an mbarrier transaction count
+  __shared__ __align__(128) float4 s_top[CRT_SMEM_TOP * 5];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int32_t n_cache = (int32_t)min(S.n_top_cache, (uint32_t)CRT_SMEM_TOP);
+  if (n_cache > 0) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_top);
+    const uint32_t bytes = (uint32_t)n_cache * 80u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(S.top_cache), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t landed = 0;
+    while (!landed) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(landed) : "r"(bar), "r"(0) : "memory");
+    }
+  }
 #endif
   int sp = 0;
   int32_t inst = -1;
@@ -376,6 +410,12 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         if (COUNT) { if (any_ray) cnt.n_inner_any++; else cnt.n_inner++; }
         const float4* nd = S.nodes + 4 * (size_t)cur;
         float4 n0, n1, n2, n3;
+        #if CRT_SMEM_TOP > 0
+        if (cur < n_cache) {
+          const float4* sn = s_top + 5 * cur;
+          n0 = sn[0]; n1 = sn[1]; n2 = sn[2]; n3 = sn[3];
+        } else
+#endif
         ld_record64(nd, n0, n1, n2, n3);
         const float c0x0 = fmaf(n0.x, r.inv.x, r.oinv.x), c0x1 = fmaf(n0.y, r.inv.x, r.oinv.x);
         const float c0y0 = fmaf(n0.z, r.inv.y, r.oinv.y), c0y1 = fmaf(n0.w, r.inv.y, r.oinv.y);
