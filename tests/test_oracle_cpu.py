@@ -369,3 +369,42 @@ def test_base_colour_texture_semantics(product_lib, oracle_lib):
     o = _oracle(d3)
     img = o.hdr(o.render(32, 32, 16))
     assert img[12:20, 12:20].mean() > 1.5                 # the environment is seen through the wall
+
+
+def test_base_lobes_are_reciprocal(oracle_lib):
+    """Without a coat, f(wi, wo) = f(wo, wi): eval returns f * cos(wi), so eval(a,b)/a.z == eval(b,a)/b.z."""
+    g = np.random.default_rng(4)
+    for preset in ("matte", "metal", "glossy"):
+        b = PRESETS[preset].to_c()
+        for _ in range(200):
+            a = g.normal(size=3); a[2] = abs(a[2]) + 0.05; a /= np.linalg.norm(a)
+            c = g.normal(size=3); c[2] = abs(c[2]) + 0.05; c /= np.linalg.norm(c)
+            o1, o2 = _f3((0, 0, 0)), _f3((0, 0, 0))
+            oracle_lib.orc_bsdf_eval(C.byref(b), _f3(a), _f3(c), 0, o1)
+            oracle_lib.orc_bsdf_eval(C.byref(b), _f3(c), _f3(a), 0, o2)
+            f1 = np.array(o1[:]) / a[2]
+            f2 = np.array(o2[:]) / c[2]
+            assert np.allclose(f1, f2, rtol=2e-4, atol=1e-6), (preset, f1, f2)
+
+
+def test_sphere_light_matches_emissive_geometry(product_lib, oracle_lib):
+    """Light sampling + MIS normalisation: a positional light of radius r and radiance L illuminates a diffuse
+    floor like an emissive sphere mesh of the same radius and radiance traced by pure path tracing
+    (the cone model uses tan(theta) = r/d, the sphere sin(theta) = r/d: 2 % apart at r/d = 0.2)."""
+    def floor_scene(with_mesh_light):
+        d = scenes.SceneDesc("light", width=24, height=24)
+        p, n, i = scenes._merge([scenes._grid_face(np.array([-20, -20, 0.0]), np.array([40, 0, 0.0]), np.array([0, 40, 0.0]),
+                                                   np.array([0, 0, 1.0]), 1)])
+        d.add((p, n, i), None, Graphic3d_BSDF(Kd=[0.7] * 3))
+        if with_mesh_light:
+            d.add(scenes.uv_sphere(0.2, 48, 24), scenes.trsf((0, 0, 1.0)), Graphic3d_BSDF(Le=[5.0, 5.0, 5.0]))
+        else:
+            d.lights = [make_light(True, (0, 0, 1.0), intensity=5.0, smoothness=0.2)]
+        d.camera = scenes.look_at((0.0, -2.0, 0.6), (0.0, 0.6, 0.0), fovy=18)
+        d.params = Graphic3d_RenderingParams(RaytracingDepth=2, RadianceClampingValue=1e9, RussianRoulette=False)
+        return d
+    a = _oracle(floor_scene(False)); b = _oracle(floor_scene(True))
+    ia = a.hdr(a.render(24, 24, 256))[:12]          # lower half of the image: floor only, below the light
+    ib = b.hdr(b.render(24, 24, 2048))[:12]         # implicit hits only: noisier, more samples
+    assert ia.mean() > 0.05
+    assert ia.mean() == pytest.approx(ib.mean(), rel=0.05)
