@@ -634,6 +634,7 @@ int crt_scene_clear(crt_context* c)
   CRT_REQUIRE(c, "null context");
   c->scene.meshes.clear();
   c->scene.instances.clear();
+  c->scene.tree_cache.clear();
   c->geometry_dirty = true;
   return CRT_OK;
 }

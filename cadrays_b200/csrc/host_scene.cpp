@@ -17,11 +17,7 @@ struct Prim {
   uint32_t id;
 };
 
-struct TreeNode {
-  float lo[3], hi[3];
-  int32_t a, b;   // inner: child node indices; leaf: first/last primitive (inclusive)
-  bool leaf;
-};
+using TreeNode = BottomTreeNode;
 
 inline float half_area(const float* lo, const float* hi)
 {
@@ -154,12 +150,7 @@ bool invert_affine(const float* m, float* out)
   return true;
 }
 
-struct MeshTree {
-  std::vector<TreeNode> nodes;
-  std::vector<uint32_t> order;   // BVH order -> caller's triangle index
-  int depth = 0;
-  uint32_t node_off = 0, vert_off = 0, tri_off = 0;
-};
+using MeshTree = BottomTree;
 
 }  // namespace
 
@@ -167,7 +158,8 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
 {
   const size_t n_mesh = scene.meshes.size();
   const size_t n_inst = scene.instances.size();
-  std::vector<MeshTree> trees(n_mesh);
+  scene.tree_cache.resize(n_mesh);
+  std::vector<MeshTree>& trees = scene.tree_cache;
   std::vector<char> used(n_mesh, 0);
   for (const Instance& in : scene.instances) {
     if (in.mesh >= n_mesh) { err = "instance refers to an unknown mesh"; return false; }
@@ -177,7 +169,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   // bottom-level trees, one per referenced mesh
 #pragma omp parallel for schedule(dynamic, 1)
   for (long mi = 0; mi < (long)n_mesh; ++mi) {
-    if (!used[mi]) continue;
+    if (!used[mi] || trees[mi].built) continue;
     const Mesh& m = scene.meshes[mi];
     const size_t nt = m.idx.size() / 3;
     std::vector<Prim> prims(nt);
@@ -191,6 +183,9 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     build_tree(prims, kBottomLeafSize, kBottomBins, trees[mi].nodes, trees[mi].depth);
     trees[mi].order.resize(nt);
     for (size_t t = 0; t < nt; ++t) trees[mi].order[t] = prims[t].id;
+    trees[mi].built = true;
+#pragma omp atomic
+    scene.trees_built++;
   }
 
   // offsets

@@ -27,9 +27,26 @@ struct Instance {
   float    xf[12];             // row-major 3x4 object -> world
 };
 
+// Bottom-level tree of one mesh, kept across commits: moving an object or changing its material
+// (ImRaytraceControls.cxx:88 SetLocation, MaterialEditor.cxx:331-337) only rebuilds the top-level tree.
+struct BottomTreeNode {
+  float lo[3], hi[3];
+  int32_t a, b;   // inner: child node indices; leaf: first/last primitive (inclusive)
+  bool leaf;
+};
+struct BottomTree {
+  std::vector<BottomTreeNode> nodes;
+  std::vector<uint32_t> order;   // BVH order -> caller's triangle index
+  int depth = 0;
+  bool built = false;
+  uint32_t node_off = 0, vert_off = 0, tri_off = 0;   // offsets inside the blob being assembled
+};
+
 struct HostScene {
   std::vector<Mesh>     meshes;
   std::vector<Instance> instances;
+  mutable std::vector<BottomTree> tree_cache;   // parallel to meshes
+  mutable uint64_t trees_built = 0;             // statistics: bottom trees built so far
 };
 
 // "CRTB" blob, version 1 -- layout documented in DESIGN.md.  64-byte header

@@ -233,3 +233,30 @@ def test_cpp_host_mirror_compiles_and_runs(tmp_path, product_lib):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "blob" in r.stdout
+
+
+def test_recommit_after_edit_equals_fresh_build(product_lib):
+    """Scene edits (SetLocation / material index) reuse the cached bottom trees; the resulting blob is the one a
+    fresh build of the edited scene gives, and undoing the edit restores the original bytes."""
+    desc = scenes.assembly(n_parts=30, target_tris=9000, width=32, height=32)
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    original = v.ExportBVH()
+    moved = scenes.trsf((1, 2, 3), (0, 1, 1), 40.0)
+    v.SetLocation(4, moved)
+    v.SetMaterialIndex(7, 2)
+    v.Update()
+    edited = v.ExportBVH()
+    assert edited != original
+    m, _, mat = desc.instances[4]
+    desc.instances[4] = (m, moved, mat)
+    m7, x7, _ = desc.instances[7]
+    desc.instances[7] = (m7, x7, 2)
+    w = V3d_View(host_only=True)
+    desc.apply(w, with_target=False)
+    assert w.ExportBVH() == edited
+    v.SetLocation(4, scenes.assembly(n_parts=30, target_tris=9000, width=32, height=32).instances[4][1])
+    v.SetMaterialIndex(7, mat if False else scenes.assembly(n_parts=30, target_tris=9000).instances[7][2])
+    v.Update()
+    assert v.ExportBVH() == original
+    v.Remove(); w.Remove()
