@@ -380,9 +380,9 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (4 * depth_max + 2), c->stream));
   const bool pers = c->persistent;
   const bool fuse = pers && c->fuse_traversal;
-  static const int g_ext = resident_grid(c, k_extend<COUNT, true>, 128);
-  static const int g_con = resident_grid(c, k_connect<COUNT, true>, 128);
-  static const int g_dual = resident_grid(c, k_trace_dual<COUNT>, 128);
+  static const int g_ext = resident_grid(c, k_extend<COUNT, true>, CRT_TRACE_BLOCK);
+  static const int g_con = resident_grid(c, k_connect<COUNT, true>, CRT_TRACE_BLOCK);
+  static const int g_dual = resident_grid(c, k_trace_dual<COUNT>, CRT_TRACE_BLOCK);
   {
     SpanGuard g(c, F_GENERATE);
     k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
@@ -391,9 +391,9 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND);
-      if (fuse && depth > 0) k_trace_dual<COUNT><<<g_dual, 128, 0, c->stream>>>(c->ds, st, depth, gc);
-      else if (pers) k_extend<COUNT, true><<<g_ext, 128, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_extend<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (fuse && depth > 0) k_trace_dual<COUNT><<<g_dual, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else if (pers) k_extend<COUNT, true><<<g_ext, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_extend<COUNT, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE);
@@ -402,8 +402,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     }
     if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT);
-      if (pers) k_connect<COUNT, true><<<g_con, 128, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_connect<COUNT, false><<<grid_for(c, 16), 128, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (pers) k_connect<COUNT, true><<<g_con, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_connect<COUNT, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
     }
   }
   {
@@ -917,10 +917,10 @@ int crt_trace_device(crt_context* c, const void* org4, const void* dir4, uint32_
 #define CRT_LAUNCH_TRACE(ANY, CNT)                                                                                   \
   do {                                                                                                               \
     if (pers) {                                                                                                      \
-      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true>, 128), (int)((n + 31u) / 32u));          \
-      k_trace<ANY, CNT, true><<<pg, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                           \
+      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true>, CRT_TRACE_BLOCK), (int)((n + 31u) / 32u));          \
+      k_trace<ANY, CNT, true><<<pg, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                           \
     } else {                                                                                                         \
-      k_trace<ANY, CNT, false><<<sgrid, 128, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                       \
+      k_trace<ANY, CNT, false><<<sgrid, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                       \
     }                                                                                                                \
   } while (0)
   if (any_hit) { if (c->stats_on) CRT_LAUNCH_TRACE(true, true); else CRT_LAUNCH_TRACE(true, false); }

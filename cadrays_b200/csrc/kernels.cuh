@@ -18,6 +18,11 @@
 #include "device_math.cuh"
 #include "host_scene.hpp"   // kTriStride, reference encodings
 
+// threads per CTA of the persistent traversal kernels
+#ifndef CRT_TRACE_BLOCK
+#define CRT_TRACE_BLOCK 128
+#endif
+
 namespace crt {
 
 constexpr int kStackSize = 72;            // 32 top + 32 bottom levels + sentinel + slack
@@ -196,17 +201,20 @@ struct SharedStack {
   int32_t* overflow;   // deeper levels spill to a private local array (rare: 2-level trees of depth > 28)
   __device__ __forceinline__ int32_t& operator[](int i) const
   {
-    return i < CRT_SMEM_STACK ? base[i * 128] : overflow[i - CRT_SMEM_STACK];
+    return i < CRT_SMEM_STACK ? base[i * CRT_TRACE_BLOCK] : overflow[i - CRT_SMEM_STACK];
   }
 };
 
+#ifndef CRT_KEEP_WORLD_RAY
+#define CRT_KEEP_WORLD_RAY 0
+#endif
 template <class Stack>
 __device__ __forceinline__ int32_t stack_pop(const Stack& stack, int& sp, Ray& r, v3 org, v3 dir)
 {
   if (sp == 0) return kDone;
   int32_t c = stack[--sp];
   if (c == kSentinel) {          // leaving an instance: back to the world-space ray
-    r.setup(org, dir);
+    r.setup(org, dir);           // (recomputed: cheaper than six more live registers, measured)
     if (sp == 0) return kDone;
     c = stack[--sp];
   }
@@ -331,7 +339,7 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   Hit hit;
   hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1; hit.inst = -1;
 #if CRT_SMEM_STACK > 0
-  __shared__ int32_t s_stack[CRT_SMEM_STACK * 128];
+  __shared__ int32_t s_stack[CRT_SMEM_STACK * CRT_TRACE_BLOCK];
   int32_t stack_overflow[kStackSize - CRT_SMEM_STACK];
   const SharedStack stack{ s_stack + threadIdx.x, stack_overflow };
 #else
@@ -935,7 +943,7 @@ struct ExtendPolicy {
 // SceneNearestHit for every active path.  PERSISTENT selects the per-lane-refill driver
 // (grid = resident CTAs) or the static one-ray-per-loop-iteration form (kept for A/B).
 template <bool COUNT, bool PERSISTENT>
-__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_active[depth];
@@ -1162,7 +1170,7 @@ struct ConnectPolicy {
 
 // SceneAnyHit for the shadow rays of this bounce; visible => add the contribution.
 template <bool COUNT, bool PERSISTENT>
-__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_shadow[depth];
@@ -1209,7 +1217,7 @@ struct DualPolicy {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, CRT_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n_ext = st.n_active[depth];

@@ -408,3 +408,33 @@ def test_deep_tree(product_lib, oracle_lib):
     view.Redraw(2)
     assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(orc.render(desc.width, desc.height, 2)))
     view.Remove()
+
+
+def test_two_contexts_are_independent(product_lib, oracle_lib):
+    """Two views in one process (different scenes, sizes, parameters) do not disturb each other."""
+    d1 = scenes.cornell_box(64, 48, depth=4, sphere_res=(12, 6))
+    d2 = scenes.materials_scene(80, 40, depth=6, sphere_res=(12, 6))
+    v1, o1 = _pair(d1)
+    v2, o2 = _pair(d2)
+    v1.Redraw(2); v2.Redraw(3); v1.Redraw(2); v2.Redraw(1)
+    assert np.array_equal(v1.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), o1.hdr(o1.render(64, 48, 4)))
+    assert np.array_equal(v2.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), o2.hdr(o2.render(80, 40, 4)))
+    v1.Remove(); v2.Remove()
+
+
+def test_full_size_env_lit_4k(product_lib):
+    """Config C4 shape: 3840x2160, environment-lit Materials.tcl geometry.  Size-independent properties only."""
+    g = np.random.default_rng(1)
+    env = (g.random((64, 128, 3)) ** 2 * 4).astype(np.float32)
+    desc = scenes.materials_scene(3840, 2160, depth=8, sphere_res=(64, 32), env=env)
+    view = V3d_View(0)
+    desc.apply(view)
+    assert view.Redraw(2) == 2
+    a = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft).copy()
+    assert a.shape == (2160, 3840, 3) and np.isfinite(a).all() and a.min() >= 0 and a.mean() > 0.05
+    view.ResetAccumulation(0)
+    view.Redraw(1); view.Redraw(1)
+    assert np.array_equal(a, view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft))     # batching-independent, deterministic
+    ldr = view.BufferDump(Graphic3d_BT_RGB)
+    assert ldr.dtype == np.uint8 and ldr.max() > 100
+    view.Remove()
