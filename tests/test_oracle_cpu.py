@@ -408,3 +408,64 @@ def test_sphere_light_matches_emissive_geometry(product_lib, oracle_lib):
     ib = b.hdr(b.render(24, 24, 2048))[:12]         # implicit hits only: noisier, more samples
     assert ia.mean() > 0.05
     assert ia.mean() == pytest.approx(ib.mean(), rel=0.05)
+
+
+def test_camera_rays_and_thin_lens(product_lib, oracle_lib):
+    """GenerateRay: centre pixel = view direction, corners span FOVy x aspect, orthographic origins on
+    the view plane, thin-lens rays meet on the focal plane."""
+    from cadrays_b200.view import Graphic3d_Camera
+    d = scenes.SceneDesc("cam", width=200, height=100)
+    d.add(scenes.box(1, 1, 1))
+    d.camera = Graphic3d_Camera(Eye=(1, 2, 3), Direction=(0, 2, 0), Up=(0, 0, 1), FOVy=60.0)
+    o = _oracle(d)
+    L = oracle_lib
+    org, dr = _f3((0, 0, 0)), _f3((0, 0, 0))
+    L.orc_camera_ray(o._h, 0.5, 0.5, 0.0, 0.0, org, dr)
+    assert org[:] == pytest.approx([1, 2, 3]) and dr[:] == pytest.approx([0, 1, 0], abs=1e-6)
+    L.orc_camera_ray(o._h, 1.0, 1.0, 0.0, 0.0, org, dr)          # top-right corner (rows are bottom-up)
+    hh = math.tan(math.radians(30)); hw = hh * 2.0
+    v = np.array([hw, 1.0, hh]); v /= np.linalg.norm(v)
+    assert dr[:] == pytest.approx(v.tolist(), abs=1e-6)
+    L.orc_camera_ray(o._h, 0.0, 0.0, 0.0, 0.0, org, dr)
+    v = np.array([-hw, 1.0, -hh]); v /= np.linalg.norm(v)
+    assert dr[:] == pytest.approx(v.tolist(), abs=1e-6)
+    # thin lens: every lens sample of one pixel passes through the same point of the focal plane
+    d.params.CameraApertureRadius, d.params.CameraFocalPlaneDist = 0.25, 4.0
+    o.set_params(d.params)
+    pts = []
+    for (a, b) in ((0.0, 0.0), (0.3, 0.1), (0.9, 0.6), (0.5, 0.95)):
+        L.orc_camera_ray(o._h, 0.8, 0.3, a, b, org, dr)
+        oo, dd = np.array(org[:]), np.array(dr[:])
+        t = (2.0 + 4.0 - oo[1]) / dd[1]                       # focal plane: 4 units along the view direction (+Y)
+        pts.append(oo + t * dd)
+        assert np.linalg.norm(oo - np.array([1, 2, 3])) <= 0.25 + 1e-6
+    assert np.allclose(pts, pts[0], atol=1e-5)
+    # orthographic: parallel rays, origins spread over Scale x Scale*aspect
+    d.camera = Graphic3d_Camera(Eye=(0, 0, 10), Direction=(0, 0, -1), Up=(0, 1, 0), IsOrthographic=True, Scale=6.0)
+    d.params.CameraApertureRadius = 0.0
+    o = _oracle(d)
+    L.orc_camera_ray(o._h, 1.0, 1.0, 0.0, 0.0, org, dr)
+    assert dr[:] == pytest.approx([0, 0, -1]) and abs(org[1]) == pytest.approx(3.0) and abs(org[0]) == pytest.approx(6.0)
+
+
+def test_environment_orientation(product_lib, oracle_lib):
+    """Lat-long lookup (SURVEY A.7, Z-up): +Z sees the top row of the image, -Z the bottom row, and the
+    columns follow atan2(y, x) + pi."""
+    env = np.zeros((8, 16, 3), np.float32)
+    env[0] = (1, 0, 0)          # top row red
+    env[7] = (0, 0, 1)          # bottom row blue
+    env[3:5, 12] = (0, 1, 0)    # u = 12.5/16 -> phi = 2 pi * 0.78 - pi = 1.77 rad (towards -x/+y... +y mostly)
+    d = scenes.SceneDesc("env", width=8, height=8)
+    d.add(scenes.box(0.1, 0.1, 0.1, origin=(100, 100, 100)))      # far away: every test ray misses
+    d.envmap = env
+    d.params = Graphic3d_RenderingParams(RaytracingDepth=1, RadianceClampingValue=1e9)
+    from cadrays_b200.view import Graphic3d_Camera
+    def look(direction, up):
+        d.camera = Graphic3d_Camera(Eye=(0, 0, 0), Direction=direction, Up=up, FOVy=5.0)
+        o = _oracle(d)
+        return o.hdr(o.render(8, 8, 1)).reshape(-1, 3).mean(0)
+    assert look((0, 0, 1), (0, 1, 0)) == pytest.approx([1, 0, 0], abs=0.05)
+    assert look((0, 0, -1), (0, 1, 0)) == pytest.approx([0, 0, 1], abs=0.05)
+    phi = 2 * math.pi * (12.5 / 16) - math.pi
+    c = look((math.cos(phi), math.sin(phi), 0.0), (0, 0, 1))
+    assert c[1] > 0.8 and c[0] < 0.05 and c[2] < 0.05
