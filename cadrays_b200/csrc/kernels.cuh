@@ -312,6 +312,9 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_INNER_EXIT
 #define CRT_INNER_EXIT 1
 #endif
+#ifndef CRT_PREFETCH
+#define CRT_PREFETCH 0
+#endif
 #ifndef CRT_SMEM_TOP
 #define CRT_SMEM_TOP 0
 #endif
@@ -438,6 +441,11 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         const bool h0 = fmaxf(te0, 0.0f) <= fminf(tx0, hit.t);
         const bool h1 = fmaxf(te1, 0.0f) <= fminf(tx1, hit.t);
         const int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+#if CRT_PREFETCH
+        // both children's records are requested while this node's slab tests run
+        if (r0 >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4 * (size_t)r0));
+        if (r1 >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4 * (size_t)r1));
+#endif
         if (h0 | h1) {
           const bool swap = h1 && (!h0 || te1 < te0);
           cur = swap ? r1 : r0;
