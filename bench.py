@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--parts", type=int, default=1000)
     ap.add_argument("--tris", type=int, default=1_000_000)
     ap.add_argument("--workload", default="assembly", choices=["assembly", "cornell", "materials", "instanced", "instanced_flat"])
+    ap.add_argument("--bvh-width", type=int, default=2, choices=[2, 4], help="2 = binary BVH (default), 4 = OCCT's optional QUAD_BVH collapse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="1920x1080x8", help="WxHxSPP sample of the workload for the CPU legs")
     return ap.parse_args()
@@ -70,6 +71,7 @@ def workload_config(args, desc):
                     f"60% diffuse / 40% glossy, 1 directional light, {args.width}x{args.height}, depth {args.depth}"
                     if args.workload == "assembly" else f"{args.workload} {args.width}x{args.height} depth {args.depth}",
         "spp_per_step_per_gpu": args.spp,
+        "bvh_width": args.bvh_width,
         "l2": "per-step working set (about 5 GB of path state + 0.12 GB of scene) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -124,9 +126,10 @@ class ClockSampler:
 
 
 def algorithmic_bytes(st: dict):
-    """64 B per inner visit, 16 B per leaf visit, 52 B per triangle test, 64 B per level switch."""
-    near = 64 * st["n_inner"] + 16 * st["n_leaf"] + 52 * st["n_tri"] + 64 * st["n_switch"]
-    anyh = 64 * st["n_inner_any"] + 16 * st["n_leaf_any"] + 52 * st["n_tri_any"] + 64 * st["n_switch_any"]
+    """an inner visit reads 16 B of node info + 24 B per child box tested (= 64 B for a binary node),
+    16 B per leaf visit, 52 B per triangle test, 64 B per level switch."""
+    near = 16 * st["n_inner"] + 24 * st["n_boxes"] + 16 * st["n_leaf"] + 52 * st["n_tri"] + 64 * st["n_switch"]
+    anyh = 16 * st["n_inner_any"] + 24 * st["n_boxes_any"] + 16 * st["n_leaf_any"] + 52 * st["n_tri_any"] + 64 * st["n_switch_any"]
     shade = (36 + 128) * st["shaded_hits"] + 32 * st["samples"]
     return near, anyh, shade
 
@@ -223,7 +226,9 @@ def run_ours(args):
     W, H, B, depth = args.width, args.height, args.spp, args.depth
     p = desc.params
     p.SamplesPerBatch = B
+    p.BvhWidth = args.bvh_width
     view.SetRenderingParams(p)
+    view.Update()
 
     stream = torch.cuda.ExternalStream(view.Stream(), device=torch.device("cuda", local))
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=f"cuda:{local}")
@@ -321,7 +326,7 @@ def run_ours(args):
             "traffic": ncu_traffic(),
             "algorithmic_bytes_per_launch": trav_b / max(trav_n, 1), "launch_ms": trav_ms / max(trav_n, 1), "launches": trav_n,
             "algorithmic_bytes_per_step": trav_b / args.steps, "traversal_ms_per_step": trav_ms / args.steps,
-            "per_ray_nearest": {"n_inner": stats["n_inner"] / nr, "n_leaf": stats["n_leaf"] / nr, "n_tri": stats["n_tri"] / nr, "n_switch": stats["n_switch"] / nr},
+            "per_ray_nearest": {"n_inner": stats["n_inner"] / nr, "n_boxes": stats["n_boxes"] / nr, "n_leaf": stats["n_leaf"] / nr, "n_tri": stats["n_tri"] / nr, "n_switch": stats["n_switch"] / nr},
             "per_ray_any": {"n_inner": stats["n_inner_any"] / na, "n_leaf": stats["n_leaf_any"] / na, "n_tri": stats["n_tri_any"] / na, "n_switch": stats["n_switch_any"] / na},
             "note": "algorithmic bytes use the reference's record sizes (SURVEY 8(d): 64 B inner visit, 16 B leaf, 52 B triangle, 64 B switch); "
                     "the scene is largely L1/L2-resident, so achieved may exceed the HBM copy peak -- see profiles/ for what binds",

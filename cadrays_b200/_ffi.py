@@ -43,7 +43,7 @@ class crt_params(C.Structure):
                 ("tone_map", C.c_int32), ("white_point", C.c_float), ("exposure", C.c_float),
                 ("env_as_background", C.c_int32), ("frame_seed0", C.c_uint32),
                 ("russian_roulette", C.c_int32), ("background", C.c_float * 3),
-                ("samples_per_batch", C.c_int32)]
+                ("samples_per_batch", C.c_int32), ("bvh_width", C.c_int32)]
 
 
 class crt_camera(C.Structure):
@@ -55,7 +55,7 @@ class crt_camera(C.Structure):
 class crt_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("rays_nearest", "rays_any", "n_inner", "n_leaf", "n_tri", "n_switch", "shaded_hits", "samples",
-                 "n_inner_any", "n_leaf_any", "n_tri_any", "n_switch_any")]
+                 "n_inner_any", "n_leaf_any", "n_tri_any", "n_switch_any", "n_boxes", "n_boxes_any")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -74,6 +74,7 @@ struct crt_context {
   bool geometry_dirty = true;
   std::vector<uint8_t> blob;
   bool has_layout = false;
+  bool quad = false;                 // the uploaded layout is the 4-wide one (crt_params.bvh_width = 4)
   std::vector<crt_bsdf> mats;
   std::vector<float> lights;         // 8 floats per light, shader form
   std::vector<float> env;            // rgba per texel
@@ -263,7 +264,7 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
   c->ds.tri_uv = c->d_tri_uv.p;
   {
     // padded copy of the first top-level nodes (breadth-first = top of the tree) for shared-memory staging
-    const uint32_t n_cache = std::min<uint32_t>(L.n_top_inner, 1024u);
+    const uint32_t n_cache = L.quad ? 0u : std::min<uint32_t>(L.n_top_inner, 1024u);
     std::vector<f4> cache((size_t)5 * std::max<uint32_t>(n_cache, 1), f4{ 0, 0, 0, 0 });
     for (uint32_t k = 0; k < n_cache; ++k)
       for (int q = 0; q < 4; ++q) cache[5 * (size_t)k + q] = L.nodes[4 * (size_t)k + q];
@@ -275,7 +276,8 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
   c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
-  if (L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
+  c->quad = L.quad;
+  if (L.quad ? 3 * (L.max_depth_top + L.max_depth_bottom) + 4 > kStackSizeQuad : L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
     return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
   if (c->l2_persist) {
     // keep nodes + triangle vertices + instance records resident in the 126 MB L2 while gigabytes of
@@ -363,7 +365,7 @@ int resident_grid(const crt_context* c, K kernel, int block)
   return c->sm_count * per_sm;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool QUAD>
 int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
 {
   PathState st;
@@ -378,11 +380,11 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   st.work_connect = st.work_extend + depth_max;
   Counters* gc = c->d_counters.p;
   CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (4 * depth_max + 2), c->stream));
-  const bool pers = c->persistent;
+  const bool pers = c->persistent || QUAD;      // the 4-wide walk exists in the persistent driver only
   const bool fuse = pers && c->fuse_traversal;
-  static const int g_ext = resident_grid(c, k_extend<COUNT, true>, CRT_TRACE_BLOCK);
-  static const int g_con = resident_grid(c, k_connect<COUNT, true>, CRT_TRACE_BLOCK);
-  static const int g_dual = resident_grid(c, k_trace_dual<COUNT>, CRT_TRACE_BLOCK);
+  static const int g_ext = resident_grid(c, k_extend<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int g_con = resident_grid(c, k_connect<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int g_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
   {
     SpanGuard g(c, F_GENERATE);
     k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
@@ -391,9 +393,9 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND);
-      if (fuse && depth > 0) k_trace_dual<COUNT><<<g_dual, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else if (pers) k_extend<COUNT, true><<<g_ext, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_extend<COUNT, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE);
@@ -402,8 +404,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
     }
     if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT);
-      if (pers) k_connect<COUNT, true><<<g_con, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_connect<COUNT, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      if (pers) k_connect<COUNT, true, QUAD><<<g_con, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      else k_connect<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
     }
   }
   {
@@ -434,7 +436,8 @@ int render_impl(crt_context* c, uint32_t n_samples)
   SpanGuard whole(c, F_RENDER);
   for (uint32_t done = 0; done < n_samples; done += batch) {
     const uint32_t nb = std::min(batch, n_samples - done);
-    rc = c->stats_on ? launch_batch<true>(c, nb, c->seeds.p + done) : launch_batch<false>(c, nb, c->seeds.p + done);
+    if (c->quad) rc = c->stats_on ? launch_batch<true, true>(c, nb, c->seeds.p + done) : launch_batch<false, true>(c, nb, c->seeds.p + done);
+    else rc = c->stats_on ? launch_batch<true, false>(c, nb, c->seeds.p + done) : launch_batch<false, false>(c, nb, c->seeds.p + done);
     if (rc) return rc;
   }
   c->next_sample += n_samples;
@@ -721,7 +724,9 @@ int crt_params_set(crt_context* c, const crt_params* p)
 {
   CRT_REQUIRE(c && p, "null argument");
   CRT_REQUIRE(p->max_depth >= 1 && p->max_depth <= 64, "max_depth out of range");
+  CRT_REQUIRE(p->bvh_width == 0 || p->bvh_width == 2 || p->bvh_width == 4, "bvh_width must be 0, 2 or 4");
   if (p->frame_seed0 != c->params.frame_seed0) c->rng_valid = false;
+  if ((p->bvh_width == 4) != (c->params.bvh_width == 4)) c->geometry_dirty = true;   // rebuilt at the next crt_commit
   c->params = *p;
   reset_accum_state(c);
   return CRT_OK;
@@ -758,7 +763,7 @@ int crt_commit(crt_context* c)
   if (c->device < 0) {   // host-only: BVH build + blob, nothing to upload
     if (c->geometry_dirty) {
       std::string err;
-      if (!build_blob(c->scene, c->blob, err)) return fail(CRT_ERR_INVALID_ARG, err);
+      if (!build_blob(c->scene, c->blob, err, c->params.bvh_width == 4 ? 4 : 2)) return fail(CRT_ERR_INVALID_ARG, err);
       c->geometry_dirty = false;
     }
     return CRT_OK;
@@ -767,7 +772,7 @@ int crt_commit(crt_context* c)
   if (rc) return rc;
   if (c->geometry_dirty) {
     std::string err;
-    if (!build_blob(c->scene, c->blob, err)) return fail(CRT_ERR_INVALID_ARG, err);
+    if (!build_blob(c->scene, c->blob, err, c->params.bvh_width == 4 ? 4 : 2)) return fail(CRT_ERR_INVALID_ARG, err);
     if ((rc = load_blob(c))) return rc;
     c->geometry_dirty = false;
     reset_accum_state(c);
@@ -916,11 +921,14 @@ int crt_trace_device(crt_context* c, const void* org4, const void* dir4, uint32_
   SpanGuard g(c, any_hit ? F_CONNECT : F_EXTEND);
 #define CRT_LAUNCH_TRACE(ANY, CNT)                                                                                   \
   do {                                                                                                               \
-    if (pers) {                                                                                                      \
-      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true>, CRT_TRACE_BLOCK), (int)((n + 31u) / 32u));          \
-      k_trace<ANY, CNT, true><<<pg, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                           \
+    if (c->quad) {                                                                                                   \
+      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true, true>, CRT_TRACE_BLOCK), (int)((n + 31u) / 32u)); \
+      k_trace<ANY, CNT, true, true><<<pg, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);         \
+    } else if (pers) {                                                                                               \
+      const int pg = std::min<int>(resident_grid(c, k_trace<ANY, CNT, true, false>, CRT_TRACE_BLOCK), (int)((n + 31u) / 32u)); \
+      k_trace<ANY, CNT, true, false><<<pg, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);        \
     } else {                                                                                                         \
-      k_trace<ANY, CNT, false><<<sgrid, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);                       \
+      k_trace<ANY, CNT, false, false><<<sgrid, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, o, d, n, h, hi, work, gc);    \
     }                                                                                                                \
   } while (0)
   if (any_hit) { if (c->stats_on) CRT_LAUNCH_TRACE(true, true); else CRT_LAUNCH_TRACE(true, false); }

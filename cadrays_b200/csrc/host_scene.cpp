@@ -127,6 +127,41 @@ void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<
   }
 }
 
+// BVH_QuadTree collapse (SURVEY A.3 "optional QUAD_BVH"; north_star: "per-mesh quad trees"): every inner
+// node adopts its grandchildren, so an inner node has 2..4 children stored contiguously.  Output nodes
+// reuse TreeNode with a = first child, b = child count - 1 for inner nodes; leaves are unchanged.
+std::vector<TreeNode> collapse_to_quad(const std::vector<TreeNode>& bin, int& depth)
+{
+  std::vector<TreeNode> quad;
+  depth = 0;
+  if (bin.empty()) return quad;
+  struct Item { int32_t bin_index, quad_index; int depth; };
+  std::vector<Item> queue;
+  quad.push_back(bin[0]);
+  queue.push_back({ 0, 0, 0 });
+  for (size_t q = 0; q < queue.size(); ++q) {
+    const Item it = queue[q];
+    const TreeNode& bn = bin[it.bin_index];
+    depth = std::max(depth, it.depth);
+    if (bn.leaf) { quad[it.quad_index] = bn; continue; }
+    int32_t kids[4];
+    int n = 0;
+    for (int32_t c : { bn.a, bn.b }) {
+      if (bin[c].leaf) kids[n++] = c;
+      else { kids[n++] = bin[c].a; kids[n++] = bin[c].b; }
+    }
+    const int32_t first = (int32_t)quad.size();
+    for (int k = 0; k < n; ++k) {
+      quad.push_back(bin[kids[k]]);
+      queue.push_back({ kids[k], first + k, it.depth + 1 });
+    }
+    TreeNode inner = bn;
+    inner.leaf = false; inner.a = first; inner.b = n - 1;
+    quad[it.quad_index] = inner;
+  }
+  return quad;
+}
+
 size_t align16(size_t x) { return (x + 15u) & ~(size_t)15u; }
 
 // Inverse of a row-major 3x4 affine matrix, computed in double.
@@ -154,8 +189,9 @@ using MeshTree = BottomTree;
 
 }  // namespace
 
-bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err)
+bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err, int bvh_width)
 {
+  const bool quad = bvh_width == 4;
   const size_t n_mesh = scene.meshes.size();
   const size_t n_inst = scene.instances.size();
   scene.tree_cache.resize(n_mesh);
@@ -188,6 +224,15 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     scene.trees_built++;
   }
 
+  // nodes as they go into the blob: the binary trees, or their 4-wide collapse
+  std::vector<std::vector<TreeNode>> emit(n_mesh);
+  for (size_t mi = 0; mi < n_mesh; ++mi) {
+    if (!used[mi]) continue;
+    int qd = 0;
+    if (quad) emit[mi] = collapse_to_quad(trees[mi].nodes, qd);
+  }
+  auto mesh_nodes = [&](size_t mi) -> const std::vector<TreeNode>& { return quad ? emit[mi] : trees[mi].nodes; };
+
   // offsets
   uint32_t n_verts = 0, n_tris = 0, n_bottom_nodes = 0;
   bool any_uv = false;
@@ -198,7 +243,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     trees[mi].node_off = n_bottom_nodes;   // rebased below once the top tree size is known
     n_verts += (uint32_t)(scene.meshes[mi].pos.size() / 3);
     n_tris += (uint32_t)(scene.meshes[mi].idx.size() / 3);
-    n_bottom_nodes += (uint32_t)trees[mi].nodes.size();
+    n_bottom_nodes += (uint32_t)mesh_nodes(mi).size();
     any_uv = any_uv || scene.meshes[mi].has_uv;
   }
 
@@ -234,6 +279,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   std::vector<TreeNode> top;
   int top_depth = 0;
   build_tree(iprims, kTopLeafSize, kTopBins, top, top_depth);
+  if (quad) top = collapse_to_quad(top, top_depth);
   const uint32_t n_top = (uint32_t)top.size();
   const uint32_t n_nodes = n_inst ? n_top + n_bottom_nodes : 0;
 
@@ -241,7 +287,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   hdr.magic = kBlobMagic; hdr.version = 1;
   hdr.n_nodes = n_nodes; hdr.n_verts = n_inst ? n_verts : 0; hdr.n_tris = n_inst ? n_tris : 0;
   hdr.n_inst = (uint32_t)n_inst; hdr.n_top_nodes = n_inst ? n_top : 0;
-  hdr.flags = any_uv ? 1u : 0u;
+  hdr.flags = (any_uv ? 1u : 0u) | (quad ? 2u : 0u);
   if (n_inst) {
     for (int k = 0; k < 3; ++k) { hdr.scene_min[k] = top[0].lo[k]; hdr.scene_max[k] = top[0].hi[k]; }
     float sx = top[0].hi[0] - top[0].lo[0], sy = top[0].hi[1] - top[0].lo[1], sz = top[0].hi[2] - top[0].lo[2];
@@ -297,8 +343,9 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     const MeshTree& mt = trees[mi];
     const Mesh& m = scene.meshes[mi];
     const uint32_t base = n_top + mt.node_off;
-    for (size_t n = 0; n < mt.nodes.size(); ++n) {
-      const TreeNode& t = mt.nodes[n];
+    const std::vector<TreeNode>& mnodes = mesh_nodes(mi);
+    for (size_t n = 0; n < mnodes.size(); ++n) {
+      const TreeNode& t = mnodes[n];
       std::memcpy(nmin + 3 * (base + n), t.lo, 12);
       std::memcpy(nmax + 3 * (base + n), t.hi, 12);
       int32_t* ni = info + 4 * (base + n);
@@ -346,6 +393,7 @@ bool parse_blob(const void* data, size_t size, BlobView& v, std::string& err)
   v.inst_meta = reinterpret_cast<const int32_t*>(base + off); off = align16(off + (size_t)16 * h.n_inst);
   if (off > size) { err = "blob truncated"; return false; }
   if (h.n_top_nodes > h.n_nodes) { err = "blob node counts inconsistent"; return false; }
+  if (h.flags & ~3u) { err = "blob: unknown flags"; return false; }
   return true;
 }
 
@@ -398,6 +446,44 @@ struct Converter {
     return self;
   }
 
+  // 4-wide layout: one recursive converter for both levels (children contiguous in the blob)
+  int32_t quad_node(int32_t node_abs, int32_t node_off, int32_t tri_off, bool top_level, int depth)
+  {
+    if (!ok) return kRefNone;
+    if (!node_ok(node_abs) || depth > 64) { err = "blob: quad tree malformed"; ok = false; return kRefNone; }
+    const int32_t* info = v.node_info + 4 * (size_t)node_abs;
+    if (top_level) out.max_depth_top = std::max(out.max_depth_top, depth);
+    else cur_depth_max = std::max(cur_depth_max, depth);
+    if (info[0] > 0) {
+      if (!top_level) { err = "blob: top-level leaf inside a bottom tree"; ok = false; return kRefNone; }
+      return top_leaf(info);
+    }
+    if (info[0] < 0) {
+      if (top_level) { err = "blob: bottom leaf inside the top tree"; ok = false; return kRefNone; }
+      const int64_t first = (int64_t)tri_off + info[1], last = (int64_t)tri_off + info[2];
+      if (first < 0 || last < first || last >= (int64_t)v.hdr.n_tris) { err = "blob: leaf range"; ok = false; return kRefNone; }
+      out.tri_verts[kTriStride * (size_t)last + 1].w = bits(1);
+      return (int32_t)(kRefLeafBit | (uint32_t)first);
+    }
+    const int k = info[2] + 1;
+    if (k < 1 || k > 4) { err = "blob: quad node child count"; ok = false; return kRefNone; }
+    const int32_t self = (int32_t)(out.nodes.size() / 8);
+    out.nodes.resize(out.nodes.size() + 8, f4{ 0, 0, 0, 0 });
+    int32_t refs[4] = { kRefNone, kRefNone, kRefNone, kRefNone };
+    float boxes[24] = { 0 };
+    for (int c = 0; c < k; ++c) {
+      const int32_t ch = node_off + info[1] + c;
+      if (!node_ok(ch)) { err = "blob: child index"; ok = false; return kRefNone; }
+      refs[c] = quad_node(ch, node_off, tri_off, top_level, depth + 1);
+      std::memcpy(boxes + 6 * c, v.node_min + 3 * (size_t)ch, 12);
+      std::memcpy(boxes + 6 * c + 3, v.node_max + 3 * (size_t)ch, 12);
+    }
+    f4* nd = &out.nodes[8 * (size_t)self];
+    std::memcpy(nd, boxes, sizeof boxes);
+    nd[6] = f4{ bits(refs[0]), bits(refs[1]), bits(refs[2]), bits(refs[3]) };
+    return self;
+  }
+
   // instance leaf of the top tree: converts (once per mesh) the bottom tree it points to
   int32_t top_leaf(const int32_t* info)
   {
@@ -407,7 +493,7 @@ struct Converter {
     auto it = mesh_root_ref.find(info[1]);
     if (it == mesh_root_ref.end()) {
       cur_depth_max = 0;
-      ref = bottom(info[1], info[1], info[3], 0);
+      ref = out.quad ? quad_node(info[1], info[1], info[3], false, 0) : bottom(info[1], info[1], info[3], 0);
       mesh_root_ref[info[1]] = ref;
       out.max_depth_bottom = std::max(out.max_depth_bottom, cur_depth_max);
     } else {
@@ -515,8 +601,9 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
     for (int r = 0; r < 3; ++r) out.inst[4 * k + r] = f4{ m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3] };
     out.inst[4 * k + 3] = f4{ Converter::bits(kRefNone), Converter::bits(v.inst_meta[4 * k]), 0.0f, 0.0f };
   }
+  out.quad = (h.flags & 2u) != 0;
   Converter c{ v, out, err };
-  out.top_root = c.top(0);
+  out.top_root = out.quad ? c.quad_node(0, 0, 0, true, 0) : c.top(0);
   return c.ok;
 }
 

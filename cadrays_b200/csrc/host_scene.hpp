@@ -82,7 +82,9 @@ constexpr int kTopBins        = 32;
 // Builds bottom BVHs per mesh (shared by all its instances), the top BVH over
 // instance world boxes, and serialises everything.  Returns false + message on
 // invalid input.
-bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err);
+// bvh_width: 2 = binary trees (default), 4 = OCCT's optional 4-wide collapse on both levels (blob flag bit 1:
+// inner node info = (0, first child, child count - 1, 0), children contiguous).
+bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err, int bvh_width = 2);
 bool parse_blob(const void* data, size_t size, BlobView& view, std::string& err);
 
 // Reference encodings of child / root references in the device layout.
@@ -117,7 +119,10 @@ struct DeviceLayout {
   std::vector<f4> inst;
   int32_t top_root = kRefNone;
   uint32_t n_tris = 0, n_inst = 0;
-  uint32_t n_top_inner = 0;    // nodes[0 .. n_top_inner) = top-level tree in breadth-first order
+  uint32_t n_top_inner = 0;    // nodes[0 .. n_top_inner) = top-level tree in breadth-first order (binary layout)
+  // quad layout (blob flag bit 1): 8 x float4 per inner node = 4 child boxes (lo.xyz, hi.xyz each, 24 floats),
+  // then (ref0..ref3) as int bits (kRefNone = no such child), then one pad float4
+  bool quad = false;
   int max_depth_top = 0, max_depth_bottom = 0;
 };
 

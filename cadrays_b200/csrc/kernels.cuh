@@ -26,6 +26,7 @@
 namespace crt {
 
 constexpr int kStackSize = 72;            // 32 top + 32 bottom levels + sentinel + slack
+constexpr int kStackSizeQuad = 104;       // 4-wide: up to 3 pushes per level, half as many levels
 constexpr int32_t kSentinel = 0x7ffffffe; // "leave the instance" marker on the stack
 constexpr int32_t kNoRef = 0x7fffffff;
 
@@ -70,6 +71,7 @@ struct DeviceParams {
 struct Counters {   // mirrors crt_stats
   unsigned long long rays_nearest, rays_any, n_inner, n_leaf, n_tri, n_switch, shaded_hits, samples;
   unsigned long long n_inner_any, n_leaf_any, n_tri_any, n_switch_any;
+  unsigned long long n_boxes, n_boxes_any;
 };
 
 struct PathState {
@@ -237,7 +239,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
   while (cur != kDone) {
     // ---- inner nodes: test both children, descend into the nearer one, push the farther
     while (cur >= 0) {
-      if (COUNT) { if (ANY) cnt.n_inner_any++; else cnt.n_inner++; }
+      if (COUNT) { if (ANY) { cnt.n_inner_any++; cnt.n_boxes_any += 2; } else { cnt.n_inner++; cnt.n_boxes += 2; } }
       const float4* nd = S.nodes + 4 * (size_t)cur;
       float4 n0, n1, n2, n3;
         ld_record64(nd, n0, n1, n2, n3);
@@ -325,7 +327,7 @@ constexpr uint32_t kChunk = CRT_CHUNK;
 
 // MODE 0: closest hit for every ray, 1: any hit for every ray, 2: per ray (Policy::load says which;
 // used by the fused "connect(d) + extend(d+1)" launch).
-template <int MODE, bool COUNT, class Policy>
+template <int MODE, bool COUNT, bool QUAD, class Policy>
 __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t n, uint32_t* work, Counters& cnt,
                                                  const Policy& pol)
 {
@@ -346,7 +348,7 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   int32_t stack_overflow[kStackSize - CRT_SMEM_STACK];
   const SharedStack stack{ s_stack + threadIdx.x, stack_overflow };
 #else
-  int32_t stack_mem[kStackSize];
+  int32_t stack_mem[QUAD ? kStackSizeQuad : kStackSize];
   const LocalStack stack{ stack_mem };
 #endif
 #if CRT_SMEM_TOP > 0
@@ -417,8 +419,8 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
     // walking inner nodes while another lane of the warp waits for its leaf / instance step (the
     // simulator tools/simt_model.py predicts fewer issue slots per ray for N around 12).
     while (cur >= 0) {
-      {
-        if (COUNT) { if (any_ray) cnt.n_inner_any++; else cnt.n_inner++; }
+      if (!QUAD) {
+        if (COUNT) { if (any_ray) { cnt.n_inner_any++; cnt.n_boxes_any += 2; } else { cnt.n_inner++; cnt.n_boxes += 2; } }
         const float4* nd = S.nodes + 4 * (size_t)cur;
         float4 n0, n1, n2, n3;
         #if CRT_SMEM_TOP > 0
@@ -453,6 +455,42 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
         } else {
           cur = stack_pop(stack, sp, r, org, dir);
         }
+      }
+      else {
+        // QUAD_BVH: 128-byte node = 4 child boxes + 4 references; all children tested, sorted by entry
+        // distance with the 5-comparator network (0,1)(2,3)(0,2)(1,3)(1,2), pushed far-to-near
+        const float4* nd = S.nodes + 8 * (size_t)cur;
+        float4 a0, a1, a2, a3, a4, a5, rf, pd;
+        ld_record64(nd, a0, a1, a2, a3);
+        ld_record64(nd + 4, a4, a5, rf, pd);
+        const float b[24] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w,
+                              a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x, a5.y, a5.z, a5.w };
+        const int32_t ref[4] = { __float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w) };
+        float te[4];
+        int32_t id[4];
+        int nbox = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x0 = fmaf(b[6 * c + 0], r.inv.x, r.oinv.x), x1 = fmaf(b[6 * c + 3], r.inv.x, r.oinv.x);
+          const float y0 = fmaf(b[6 * c + 1], r.inv.y, r.oinv.y), y1 = fmaf(b[6 * c + 4], r.inv.y, r.oinv.y);
+          const float z0 = fmaf(b[6 * c + 2], r.inv.z, r.oinv.z), z1 = fmaf(b[6 * c + 5], r.inv.z, r.oinv.z);
+          const float e = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+          const float x = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+          const bool present = ref[c] != kNoRef;
+          const bool h = present && fmaxf(e, 0.0f) <= fminf(x, hit.t);
+          te[c] = h ? e : 3.0e38f;
+          id[c] = h ? ref[c] : kNoRef;
+          nbox += present ? 1 : 0;
+        }
+        if (COUNT) { if (any_ray) { cnt.n_inner_any++; cnt.n_boxes_any += nbox; } else { cnt.n_inner++; cnt.n_boxes += nbox; } }
+#define CRT_CSWAP(i, j) { const bool sw = te[j] < te[i]; const float tf = sw ? te[j] : te[i]; te[j] = sw ? te[i] : te[j]; te[i] = tf; \
+                          const int32_t ti = sw ? id[j] : id[i]; id[j] = sw ? id[i] : id[j]; id[i] = ti; }
+        CRT_CSWAP(0, 1) CRT_CSWAP(2, 3) CRT_CSWAP(0, 2) CRT_CSWAP(1, 3) CRT_CSWAP(1, 2)
+#undef CRT_CSWAP
+        if (id[3] != kNoRef) stack[sp++] = id[3];
+        if (id[2] != kNoRef) stack[sp++] = id[2];
+        if (id[1] != kNoRef) stack[sp++] = id[1];
+        cur = id[0] != kNoRef ? id[0] : stack_pop(stack, sp, r, org, dir);
       }
 #if CRT_INNER_EXIT > 1
       {
@@ -855,11 +893,11 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool pred)
 __device__ __forceinline__ void flush_counters(Counters* g, const Counters& c)
 {
   // warp-reduce then one atomic per warp and field
-  unsigned long long v[12] = { c.rays_nearest, c.rays_any, c.n_inner, c.n_leaf, c.n_tri, c.n_switch, c.shaded_hits, c.samples,
-                               c.n_inner_any, c.n_leaf_any, c.n_tri_any, c.n_switch_any };
+  unsigned long long v[14] = { c.rays_nearest, c.rays_any, c.n_inner, c.n_leaf, c.n_tri, c.n_switch, c.shaded_hits, c.samples,
+                               c.n_inner_any, c.n_leaf_any, c.n_tri_any, c.n_switch_any, c.n_boxes, c.n_boxes_any };
   unsigned long long* out = reinterpret_cast<unsigned long long*>(g);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) {
+  for (int k = 0; k < 14; ++k) {
     unsigned long long x = v[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -950,7 +988,7 @@ struct ExtendPolicy {
 
 // SceneNearestHit for every active path.  PERSISTENT selects the per-lane-refill driver
 // (grid = resident CTAs) or the static one-ray-per-loop-iteration form (kept for A/B).
-template <bool COUNT, bool PERSISTENT>
+template <bool COUNT, bool PERSISTENT, bool QUAD>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
@@ -959,7 +997,7 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
   Counters cnt = {};
   if (PERSISTENT) {
     ExtendPolicy pol{ st, q };
-    trace_persistent<0, COUNT>(S, n, st.work_extend + depth, cnt, pol);
+    trace_persistent<0, COUNT, QUAD>(S, n, st.work_extend + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const uint32_t slot = ld_stream(&q[i]);
@@ -1177,7 +1215,7 @@ struct ConnectPolicy {
 };
 
 // SceneAnyHit for the shadow rays of this bounce; visible => add the contribution.
-template <bool COUNT, bool PERSISTENT>
+template <bool COUNT, bool PERSISTENT, bool QUAD>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
@@ -1185,7 +1223,7 @@ k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
   Counters cnt = {};
   if (PERSISTENT) {
     ConnectPolicy pol{ st };
-    trace_persistent<1, COUNT>(S, n, st.work_connect + depth, cnt, pol);
+    trace_persistent<1, COUNT, QUAD>(S, n, st.work_connect + depth, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const float4 o = ld_stream(&st.sh_o[i]), d = ld_stream(&st.sh_d[i]);
@@ -1224,7 +1262,7 @@ struct DualPolicy {
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool QUAD>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
@@ -1232,7 +1270,7 @@ k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
   const uint32_t n_sh = st.n_shadow[depth - 1];
   Counters cnt = {};
   DualPolicy pol{ ExtendPolicy{ st, st.queue[depth & 1] }, ConnectPolicy{ st }, n_ext };
-  trace_persistent<2, COUNT>(S, n_ext + n_sh, st.work_extend + depth, cnt, pol);
+  trace_persistent<2, COUNT, QUAD>(S, n_ext + n_sh, st.work_extend + depth, cnt, pol);
   if (COUNT) flush_counters(gcnt, cnt);
 }
 
@@ -1313,15 +1351,15 @@ struct TracePolicy {
 };
 
 // Batch SceneNearestHit / SceneAnyHit on caller rays (parity hook crt_trace).
-template <bool ANY, bool COUNT, bool PERSISTENT>
-__global__ void __launch_bounds__(128)
+template <bool ANY, bool COUNT, bool PERSISTENT, bool QUAD>
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK)
 k_trace(DeviceScene S, const float4* __restrict__ org, const float4* __restrict__ dir, uint32_t n,
         float4* __restrict__ hit4, int32_t* __restrict__ hit_inst, uint32_t* work, Counters* gcnt)
 {
   Counters cnt = {};
   TracePolicy<ANY> pol{ org, dir, hit4, hit_inst, S.tri_verts };
   if (PERSISTENT) {
-    trace_persistent<ANY ? 1 : 0, COUNT>(S, n, work, cnt, pol);
+    trace_persistent<ANY ? 1 : 0, COUNT, QUAD>(S, n, work, cnt, pol);
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       v3 o, d; float tmax; bool unused = false;

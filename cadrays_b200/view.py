@@ -164,6 +164,7 @@ class Graphic3d_RenderingParams:
     RussianRoulette: bool = True
     BackgroundColor: tuple = (0.0, 0.0, 0.0)
     SamplesPerBatch: int = 0
+    BvhWidth: int = 2             # 4 = OCCT's optional QUAD_BVH collapse (scene is rebuilt at the next Update)
 
     def to_c(self) -> crt_params:
         if self.Method != Graphic3d_RM_RAYTRACING or not self.IsGlobalIlluminationEnabled:
@@ -186,6 +187,7 @@ class Graphic3d_RenderingParams:
         p.russian_roulette = int(self.RussianRoulette)
         p.background[:] = [float(v) for v in self.BackgroundColor]
         p.samples_per_batch = int(self.SamplesPerBatch)
+        p.bvh_width = int(self.BvhWidth)
         return p
 
 

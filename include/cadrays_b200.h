@@ -110,6 +110,8 @@ typedef struct crt_params {
   int32_t  russian_roulette; /* 1 = roulette after depth 3             */
   float    background[3];    /* colour shown by primary rays that miss when the map is hidden */
   int32_t  samples_per_batch;/* samples per pixel kept in flight per wave; 0 = auto */
+  int32_t  bvh_width;        /* 0 or 2 = binary BVH (default); 4 = OCCT's optional QUAD_BVH collapse.
+                                Changing it rebuilds the scene at the next crt_commit. */
 } crt_params;
 
 /* Graphic3d_Camera as CADRays sets it (src/Launcher/AppViewer.cxx:947,993-1042;
@@ -127,7 +129,8 @@ typedef struct crt_camera {
 /* Work counters of the traversal kernels since the last crt_stats_reset.
  * Filled only while crt_stats_enable(ctx, 1) is active (instrumented build of
  * the SAME kernels); used to compute the algorithmic bytes of SURVEY 8(d):
- *   bytes = 64*n_inner + 16*n_leaf + 52*n_tri + 64*n_switch  (+ shading). */
+ *   bytes = 16*n_inner + 24*n_boxes + 16*n_leaf + 52*n_tri + 64*n_switch  (+ shading)
+ *         = 64*n_inner + ... for binary trees (2 boxes per inner visit). */
 typedef struct crt_stats {
   uint64_t rays_nearest;
   uint64_t rays_any;
@@ -141,6 +144,8 @@ typedef struct crt_stats {
   uint64_t n_leaf_any;
   uint64_t n_tri_any;
   uint64_t n_switch_any;
+  uint64_t n_boxes;       /* child boxes tested by closest-hit rays (2 per binary node, 2..4 per quad node) */
+  uint64_t n_boxes_any;   /* the same for any-hit rays */
 } crt_stats;
 
 /* -------------------------------- lifetime -------------------------------- */

@@ -234,7 +234,10 @@ orc_scene* orc_scene_from_blob(const void* blob, size_t size)
     int st[ORC_STACK]; int hd = 0; st[0] = root;
     while (hd >= 0) {
       const int32_t* ni = s->node_info + 4 * st[hd--];
-      if (ni[0] == 0) { st[++hd] = root + ni[1]; st[++hd] = root + ni[2]; }
+      if (ni[0] == 0) {
+        if (h->flags & 2u) { for (int c = 0; c <= ni[2]; ++c) st[++hd] = root + ni[1] + c; }
+        else { st[++hd] = root + ni[1]; st[++hd] = root + ni[2]; }
+      }
       else if (ni[2] > mx) mx = ni[2];
     }
     s->inst_geom[3 * k] = info[2]; s->inst_geom[3 * k + 1] = info[3]; s->inst_geom[3 * k + 2] = mx + 1;
@@ -460,25 +463,47 @@ static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit,
   ray_t world, cur;
   ray_setup(&world, org, dir);
   cur = world;
-  uint64_t n_inner = 0, n_leaf = 0, n_tri = 0, n_switch = 0;
+  uint64_t n_inner = 0, n_leaf = 0, n_tri = 0, n_switch = 0, n_boxes = 0;
   int found = 0;
   for (;;) {
     const int32_t* info = s->node_info + 4 * node;
     if (info[0] == 0) {                                   /* inner node */
       ++n_inner; ORC_EVENT(1);
-      int l = node_off + info[1], r = node_off + info[2];
-      float tl, tr;
-      int hl = slab(&cur, s->node_min + 3 * l, s->node_max + 3 * l, hit->t, &tl);
-      int hr = slab(&cur, s->node_min + 3 * r, s->node_max + 3 * r, hit->t, &tr);
-      if (hl && hr) {
-        int nearer = (tr < tl) ? r : l;
-        int farther = (tr < tl) ? l : r;
-        stack[++head] = farther;
-        node = nearer;
-        continue;
+      if (s->hdr.flags & 2u) {
+        /* QUAD_BVH: up to 4 contiguous children, all tested, sorted by entry distance with
+         * the 5-comparator network (0,1)(2,3)(0,2)(1,3)(1,2) (swap when the later entry is strictly nearer),
+         * pushed far-to-near */
+        const int first = node_off + info[1], k = info[2] + 1;
+        float te[4]; int id[4];
+        for (int c = 0; c < 4; ++c) {
+          te[c] = 3.0e38f; id[c] = -1;
+          if (c < k) {
+            float t;
+            if (slab(&cur, s->node_min + 3 * (first + c), s->node_max + 3 * (first + c), hit->t, &t)) { te[c] = t; id[c] = first + c; }
+          }
+        }
+        n_boxes += (uint64_t)k;
+#define ORC_CSWAP(i, j) do { if (te[j] < te[i]) { float tf = te[i]; te[i] = te[j]; te[j] = tf; int ti = id[i]; id[i] = id[j]; id[j] = ti; } } while (0)
+        ORC_CSWAP(0, 1); ORC_CSWAP(2, 3); ORC_CSWAP(0, 2); ORC_CSWAP(1, 3); ORC_CSWAP(1, 2);
+#undef ORC_CSWAP
+        for (int c = 3; c >= 1; --c) if (id[c] >= 0) stack[++head] = id[c];
+        if (id[0] >= 0) { node = id[0]; continue; }
+      } else {
+        int l = node_off + info[1], r = node_off + info[2];
+        float tl, tr;
+        int hl = slab(&cur, s->node_min + 3 * l, s->node_max + 3 * l, hit->t, &tl);
+        int hr = slab(&cur, s->node_min + 3 * r, s->node_max + 3 * r, hit->t, &tr);
+        n_boxes += 2;
+        if (hl && hr) {
+          int nearer = (tr < tl) ? r : l;
+          int farther = (tr < tl) ? l : r;
+          stack[++head] = farther;
+          node = nearer;
+          continue;
+        }
+        if (hl) { node = l; continue; }
+        if (hr) { node = r; continue; }
       }
-      if (hl) { node = l; continue; }
-      if (hr) { node = r; continue; }
     } else if (info[0] < 0) {                             /* bottom-level leaf */
       ++n_leaf; ORC_EVENT(3 + (info[2] - info[1] + 1));
       for (int i = info[1]; i <= info[2]; ++i) {
@@ -508,8 +533,8 @@ static int traverse(const orc_scene* s, v3 org, v3 dir, float tmax, int any_hit,
   }
 done:
   if (st) {
-    if (any_hit) { st->n_inner_any += n_inner; st->n_leaf_any += n_leaf; st->n_tri_any += n_tri; st->n_switch_any += n_switch; }
-    else { st->n_inner += n_inner; st->n_leaf += n_leaf; st->n_tri += n_tri; st->n_switch += n_switch; }
+    if (any_hit) { st->n_inner_any += n_inner; st->n_leaf_any += n_leaf; st->n_tri_any += n_tri; st->n_switch_any += n_switch; st->n_boxes_any += n_boxes; }
+    else { st->n_inner += n_inner; st->n_leaf += n_leaf; st->n_tri += n_tri; st->n_switch += n_switch; st->n_boxes += n_boxes; }
   }
   return found;
 }
@@ -1154,6 +1179,7 @@ void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sampl
           total.n_switch += local.n_switch; total.shaded_hits += local.shaded_hits;
           total.n_inner_any += local.n_inner_any; total.n_leaf_any += local.n_leaf_any;
           total.n_tri_any += local.n_tri_any; total.n_switch_any += local.n_switch_any;
+          total.n_boxes += local.n_boxes; total.n_boxes_any += local.n_boxes_any;
         }
       }
     }
@@ -1163,6 +1189,7 @@ void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sampl
       stats->n_switch += total.n_switch; stats->shaded_hits += total.shaded_hits;
       stats->n_inner_any += total.n_inner_any; stats->n_leaf_any += total.n_leaf_any;
       stats->n_tri_any += total.n_tri_any; stats->n_switch_any += total.n_switch_any;
+      stats->n_boxes += total.n_boxes; stats->n_boxes_any += total.n_boxes_any;
       stats->samples += (uint64_t)w * h;
     }
   }

@@ -438,3 +438,34 @@ def test_full_size_env_lit_4k(product_lib):
     ldr = view.BufferDump(Graphic3d_BT_RGB)
     assert ldr.dtype == np.uint8 and ldr.max() > 100
     view.Remove()
+
+
+@pytest.mark.parametrize("which", ["cornell", "assembly", "instanced"])
+def test_quad_bvh_parity(which, product_lib, oracle_lib):
+    """crt_params.bvh_width = 4: the kernels walk the 4-wide collapse exactly as the oracle does (same sorting
+    network, same push order): hits, work counters and images are bit-equal."""
+    desc = SCENES[which]()
+    desc.params.BvhWidth = 4
+    view, orc = _pair(desc)
+    lo, hi = _scene_box(view.ExportBVH())
+    org, d = scenes.random_rays(100_000, lo, hi, seed=31)
+    view.EnableStats(True); view.ResetStats()
+    g = view.Trace(org, d)
+    gs = view.Stats()
+    view.EnableStats(False)
+    o = orc.trace(org, d, stats=True)
+    for x, y in zip(g, o[:5]):
+        assert np.array_equal(x, y)
+    for k in ("n_inner", "n_boxes", "n_leaf", "n_tri", "n_switch"):
+        assert gs[k] == o[5][k], k
+    tmax = np.random.default_rng(3).uniform(0.01, float(np.linalg.norm(hi - lo)), size=org.shape[0]).astype(np.float32)
+    assert np.array_equal(view.Trace(org, d, tmax, any_hit=True)[0], orc.trace(org, d, tmax, any_hit=True)[0])
+    view.Redraw(6)
+    acc = orc.render(desc.width, desc.height, 6)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc))
+    # switching back to the binary tree rebuilds the scene and restarts accumulation
+    desc.params.BvhWidth = 2
+    view.SetRenderingParams(desc.params)
+    view.Update()
+    assert not (np.frombuffer(view.ExportBVH(), np.uint32, 8)[7] & 2)
+    view.Remove()

@@ -31,9 +31,9 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_ffi.crt_bsdf) == 128
     assert C.sizeof(_ffi.crt_light) == 32
-    assert C.sizeof(_ffi.crt_stats) == 96
+    assert C.sizeof(_ffi.crt_stats) == 112
     assert C.sizeof(_ffi.crt_camera) == 52
-    assert C.sizeof(_ffi.crt_params) == 64
+    assert C.sizeof(_ffi.crt_params) == 68
 
 
 def test_no_device_fails_loudly(product_lib):
@@ -260,3 +260,54 @@ def test_recommit_after_edit_equals_fresh_build(product_lib):
     v.Update()
     assert v.ExportBVH() == original
     v.Remove(); w.Remove()
+
+
+def test_quad_bvh_blob(product_lib, oracle_lib):
+    """bvh_width = 4 (OCCT's optional QUAD_BVH collapse): inner nodes have 2..4 contiguous children that are
+    the binary tree's grandchildren; the oracle finds the same hits through it as through the binary tree."""
+    from oracle.oracle_ffi import OracleScene
+    desc = scenes.assembly(n_parts=40, target_tris=20000, width=32, height=32)
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    binary = v.ExportBVH()
+    desc.params.BvhWidth = 4
+    v.SetRenderingParams(desc.params)
+    v.Update()
+    quad = v.ExportBVH()
+    bq, bb = _parse_blob(quad), _parse_blob(binary)
+    assert bq["hdr"]["flags"] & 2 and not bb["hdr"]["flags"] & 2
+    assert bq["hdr"]["n_nodes"] < bb["hdr"]["n_nodes"]
+    info, bmin, bmax = bq["info"], bq["bmin"], bq["bmax"]
+    counts = []
+    def walk(root, off, top):
+        stack = [root]
+        while stack:
+            n = stack.pop()
+            x, y, z, w = info[n]
+            if x == 0:
+                k = z + 1
+                assert 2 <= k <= 4
+                counts.append(k)
+                for c in range(k):
+                    ch = off + y + c
+                    assert (bmin[ch] >= bmin[n] - 1e-6).all() and (bmax[ch] <= bmax[n] + 1e-6).all()
+                    stack.append(ch)
+            elif x > 0:
+                assert top
+                walk(y, y, False)
+            else:
+                assert not top and 0 < z - y + 1 <= 5
+    walk(0, 0, True)
+    assert np.mean(counts) > 2.5
+    ob, oq = OracleScene(binary), OracleScene(quad)
+    org, d = scenes.random_rays(20000, bq["hdr"]["min"], bq["hdr"]["max"], seed=8)
+    a = ob.trace(org, d, stats=True)
+    b = oq.trace(org, d, stats=True)
+    same = (a[0] == b[0]) & (a[1] == b[1])
+    assert same.mean() > 0.999                                  # only coplanar near-ties may resolve differently
+    assert np.allclose(a[2][same], b[2][same], rtol=1e-6)
+    assert b[5]["n_inner"] < 0.9 * a[5]["n_inner"]              # fewer dependent node steps
+    assert a[5]["n_boxes"] == 2 * a[5]["n_inner"] and b[5]["n_boxes"] > 2.5 * b[5]["n_inner"]
+    s = oq.trace(org, d, any_hit=True)
+    assert np.array_equal(s[0] == 0, b[0] >= 0)
+    v.Remove()
