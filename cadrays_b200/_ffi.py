@@ -43,7 +43,8 @@ class crt_params(C.Structure):
                 ("tone_map", C.c_int32), ("white_point", C.c_float), ("exposure", C.c_float),
                 ("env_as_background", C.c_int32), ("frame_seed0", C.c_uint32),
                 ("russian_roulette", C.c_int32), ("background", C.c_float * 3),
-                ("samples_per_batch", C.c_int32), ("bvh_width", C.c_int32)]
+                ("samples_per_batch", C.c_int32), ("bvh_width", C.c_int32),
+                ("adaptive_sampling", C.c_int32), ("adaptive_tiles", C.c_int32)]
 
 
 class crt_camera(C.Structure):
@@ -91,6 +92,8 @@ PROTOTYPES = {
     "crt_resize": (C.c_int, [_ctx, C.c_uint32, C.c_uint32]),
     "crt_commit": (C.c_int, [_ctx]),
     "crt_render": (C.c_int, [_ctx, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "crt_adaptive_tiles_get": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32,
+                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "crt_render_async": (C.c_int, [_ctx, C.c_uint32]),
     "crt_sync": (C.c_int, [_ctx]),
     "crt_reset_accumulation": (C.c_int, [_ctx, C.c_uint64]),

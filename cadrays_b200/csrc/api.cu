@@ -110,6 +110,15 @@ struct crt_context {
   uint64_t first_sample = 0, next_sample = 0;
   uint32_t rng_hi = 0, rng_lo = 0; uint64_t rng_index = 0; bool rng_valid = false;
 
+  // adaptive screen sampling (crt_params.adaptive_sampling): per-tile state, see kernels.cuh
+  DevBuf<uint32_t> ad_count, ad_err, ad_cum, ad_qoff, ad_seeds;
+  DevBuf<float> ad_even;
+  std::vector<uint32_t> ad_h_seeds;  // frame seeds of sample indices first_sample + [0, size)
+  size_t ad_seeds_uploaded = 0;
+  uint64_t ad_bound = 0;             // upper bound of any tile's sample count after the waves enqueued so far
+  uint32_t ad_wave = 0;
+  bool ad_clear = true;              // state must be zeroed before the next adaptive wave
+
   // read-back staging
   DevBuf<uint8_t> d_ldr;
   DevBuf<float> d_hdr;
@@ -183,6 +192,7 @@ struct SpanGuard {
 void reset_accum_state(crt_context* c)
 {
   c->next_sample = c->first_sample;
+  c->ad_clear = true;
   if (c->device >= 0 && c->accum && c->width && c->height)
     cudaMemsetAsync(c->accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream);
 }
@@ -218,10 +228,8 @@ void update_device_params(crt_context* c)
   P.tiles_y = (c->height + 3u) / 4u;
 }
 
-int ensure_path_state(crt_context* c, uint32_t batch)
+int ensure_path_slots(crt_context* c, uint64_t need)
 {
-  const uint64_t per_sample = (uint64_t)c->dp.tiles_x * c->dp.tiles_y * 32u;
-  const uint64_t need = per_sample * batch;
   if (need > 0x7fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
   if (need <= c->state_capacity) return CRT_OK;
   const size_t n = (size_t)need;
@@ -231,6 +239,11 @@ int ensure_path_state(crt_context* c, uint32_t batch)
   CRT_CUDA(c->sh_o.ensure(n)); CRT_CUDA(c->sh_d.ensure(n)); CRT_CUDA(c->sh_c.ensure(n));
   c->state_capacity = (uint32_t)need;
   return CRT_OK;
+}
+
+int ensure_path_state(crt_context* c, uint32_t batch)
+{
+  return ensure_path_slots(c, (uint64_t)c->dp.tiles_x * c->dp.tiles_y * 32u * batch);
 }
 
 uint32_t auto_batch(const crt_context* c)
@@ -365,8 +378,10 @@ int resident_grid(const crt_context* c, K kernel, int block)
   return c->sm_count * per_sm;
 }
 
+// One wave: n_batch samples of every pixel, or (adaptive != nullptr) `n_batch` tile samples dealt out by
+// k_adaptive_allocate.
 template <bool COUNT, bool QUAD>
-int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
+int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, const AdaptiveState* adaptive = nullptr)
 {
   PathState st;
   st.ray_o = c->ray_o.p; st.ray_d = c->ray_d.p; st.thr = c->thr.p; st.rad = c->rad.p;
@@ -387,7 +402,8 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   static const int g_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
   {
     SpanGuard g(c, F_GENERATE);
-    k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
+    if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, d_seeds, n_batch);
+    else k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
   }
   for (int depth = 0; depth < depth_max; ++depth) {
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
@@ -410,9 +426,66 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds)
   }
   {
     SpanGuard g(c, F_RESOLVE);
-    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
+    if (adaptive) k_resolve_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, c->accum, COUNT ? gc : nullptr);
+    else k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
   }
   CRT_CUDA(cudaGetLastError());
+  return CRT_OK;
+}
+
+int dispatch_batch(crt_context* c, uint32_t n, const uint32_t* d_seeds, const AdaptiveState* adaptive)
+{
+  if (c->quad) return c->stats_on ? launch_batch<true, true>(c, n, d_seeds, adaptive) : launch_batch<false, true>(c, n, d_seeds, adaptive);
+  return c->stats_on ? launch_batch<true, false>(c, n, d_seeds, adaptive) : launch_batch<false, false>(c, n, d_seeds, adaptive);
+}
+
+// Adaptive screen sampling: n_samples x adaptive_tiles tile samples, in waves of at most
+// samples-per-batch x (number of tiles); each wave is dealt out on the device from the error
+// estimates the previous wave left (kernels.cuh).
+int render_adaptive(crt_context* c, uint32_t n_samples)
+{
+  const uint32_t ntx = (c->width + kAdaptiveTile - 1) / kAdaptiveTile, nty = (c->height + kAdaptiveTile - 1) / kAdaptiveTile;
+  const uint32_t nt = ntx * nty;
+  const uint64_t per_unit = c->params.adaptive_tiles > 0 ? (uint64_t)c->params.adaptive_tiles : nt;
+  const uint64_t wave_cap = (uint64_t)auto_batch(c) * nt;
+  if (wave_cap * kAdaptiveSlots > 0x7fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
+  int rc = ensure_path_slots(c, std::min<uint64_t>(wave_cap, per_unit * n_samples) * kAdaptiveSlots);
+  if (rc) return rc;
+  CRT_CUDA(c->ad_count.ensure(nt)); CRT_CUDA(c->ad_err.ensure(nt));
+  CRT_CUDA(c->ad_cum.ensure(nt + 1)); CRT_CUDA(c->ad_qoff.ensure(nt + 1));
+  CRT_CUDA(c->ad_even.ensure((size_t)c->width * c->height));
+  if (c->ad_clear) {
+    CRT_CUDA(cudaMemsetAsync(c->ad_count.p, 0, sizeof(uint32_t) * nt, c->stream));
+    CRT_CUDA(cudaMemsetAsync(c->ad_err.p, 0, sizeof(uint32_t) * nt, c->stream));
+    CRT_CUDA(cudaMemsetAsync(c->ad_even.p, 0, sizeof(float) * (size_t)c->width * c->height, c->stream));
+    c->ad_h_seeds.clear(); c->ad_seeds_uploaded = 0; c->ad_bound = 0; c->ad_wave = 0;
+    c->ad_clear = false;
+  }
+  AdaptiveState A;
+  A.count = c->ad_count.p; A.err = c->ad_err.p; A.cum = c->ad_cum.p; A.qoff = c->ad_qoff.p; A.even = c->ad_even.p;
+  A.ntx = ntx; A.nty = nty; A.nt = nt; A.first_parity = (uint32_t)(c->first_sample & 1u);
+  SpanGuard whole(c, F_RENDER);
+  for (uint64_t left = per_unit * n_samples; left > 0;) {
+    const uint32_t budget = (uint32_t)std::min<uint64_t>(left, wave_cap);
+    // no tile can receive more than 32 * budget / nt + 1 samples in a wave (weights are clamped to a 1:32 range)
+    c->ad_bound += 32ull * budget / nt + 2;
+    if (c->ad_bound > (1ull << 26)) return fail(CRT_ERR_INVALID_ARG, "adaptive accumulation too long; reset it");
+    while (c->ad_h_seeds.size() < c->ad_bound) c->ad_h_seeds.push_back(frame_seed(c, c->first_sample + c->ad_h_seeds.size()));
+    if (c->ad_seeds.n < c->ad_h_seeds.size()) {
+      // the wave in flight may still read the old table
+      CRT_CUDA(cudaStreamSynchronize(c->stream));
+      CRT_CUDA(c->ad_seeds.ensure(std::max<size_t>(2 * c->ad_h_seeds.size(), 4096)));
+      c->ad_seeds_uploaded = 0;
+    }
+    CRT_CUDA(cudaMemcpyAsync(c->ad_seeds.p + c->ad_seeds_uploaded, c->ad_h_seeds.data() + c->ad_seeds_uploaded,
+                             sizeof(uint32_t) * (c->ad_h_seeds.size() - c->ad_seeds_uploaded), cudaMemcpyHostToDevice, c->stream));
+    c->ad_seeds_uploaded = c->ad_h_seeds.size();
+    k_adaptive_allocate<<<1, 1024, 0, c->stream>>>(A, c->dp, budget, c->ad_wave);
+    if ((rc = dispatch_batch(c, budget, c->ad_seeds.p, &A))) return rc;
+    c->ad_wave++;
+    left -= budget;
+  }
+  c->next_sample += n_samples;
   return CRT_OK;
 }
 
@@ -426,9 +499,10 @@ int render_impl(crt_context* c, uint32_t n_samples)
   if ((rc = upload_tables(c))) return rc;
   update_device_params(c);
   if (n_samples == 0) return CRT_OK;
+  CRT_CUDA(c->counters.ensure(4 * 64 + 8));
+  if (c->params.adaptive_sampling) return render_adaptive(c, n_samples);
   const uint32_t batch = std::min(auto_batch(c), n_samples);
   if ((rc = ensure_path_state(c, batch))) return rc;
-  CRT_CUDA(c->counters.ensure(4 * 64 + 8));
   CRT_CUDA(c->seeds.ensure(n_samples));
   c->h_seeds.resize(n_samples);
   for (uint32_t k = 0; k < n_samples; ++k) c->h_seeds[k] = frame_seed(c, c->next_sample + k);
@@ -436,9 +510,7 @@ int render_impl(crt_context* c, uint32_t n_samples)
   SpanGuard whole(c, F_RENDER);
   for (uint32_t done = 0; done < n_samples; done += batch) {
     const uint32_t nb = std::min(batch, n_samples - done);
-    if (c->quad) rc = c->stats_on ? launch_batch<true, true>(c, nb, c->seeds.p + done) : launch_batch<false, true>(c, nb, c->seeds.p + done);
-    else rc = c->stats_on ? launch_batch<true, false>(c, nb, c->seeds.p + done) : launch_batch<false, false>(c, nb, c->seeds.p + done);
-    if (rc) return rc;
+    if ((rc = dispatch_batch(c, nb, c->seeds.p + done, nullptr))) return rc;
   }
   c->next_sample += n_samples;
   return CRT_OK;
@@ -552,6 +624,7 @@ void crt_destroy(crt_context* c)
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();
   c->queue0.release(); c->queue1.release(); c->counters.release(); c->seeds.release();
   c->accum_internal.release(); c->d_ldr.release(); c->d_hdr.release(); c->d_counters.release();
+  c->ad_count.release(); c->ad_err.release(); c->ad_cum.release(); c->ad_qoff.release(); c->ad_seeds.release(); c->ad_even.release();
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -725,6 +798,7 @@ int crt_params_set(crt_context* c, const crt_params* p)
   CRT_REQUIRE(c && p, "null argument");
   CRT_REQUIRE(p->max_depth >= 1 && p->max_depth <= 64, "max_depth out of range");
   CRT_REQUIRE(p->bvh_width == 0 || p->bvh_width == 2 || p->bvh_width == 4, "bvh_width must be 0, 2 or 4");
+  CRT_REQUIRE(p->adaptive_tiles >= 0, "adaptive_tiles must not be negative");
   if (p->frame_seed0 != c->params.frame_seed0) c->rng_valid = false;
   if ((p->bvh_width == 4) != (c->params.bvh_width == 4)) c->geometry_dirty = true;   // rebuilt at the next crt_commit
   c->params = *p;
@@ -800,6 +874,29 @@ int crt_render(crt_context* c, uint32_t n, uint64_t* out_total)
   if (rc) return rc;
   CRT_CUDA(cudaStreamSynchronize(c->stream));
   if (out_total) *out_total = c->next_sample - c->first_sample;
+  return CRT_OK;
+}
+
+int crt_adaptive_tiles_get(crt_context* c, uint32_t* counts, uint32_t* errors, uint32_t capacity, uint32_t* out_tx, uint32_t* out_ty)
+{
+  CRT_REQUIRE(c, "null context");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const uint32_t ntx = (c->width + kAdaptiveTile - 1) / kAdaptiveTile, nty = (c->height + kAdaptiveTile - 1) / kAdaptiveTile;
+  if (out_tx) *out_tx = ntx;
+  if (out_ty) *out_ty = nty;
+  if (!counts && !errors) return CRT_OK;
+  CRT_REQUIRE(capacity >= ntx * nty, "capacity is smaller than the number of tiles");
+  const bool live = !c->ad_clear && c->ad_count.p && c->ad_count.n >= (size_t)ntx * nty;
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  if (counts) {
+    if (live) CRT_CUDA(cudaMemcpy(counts, c->ad_count.p, sizeof(uint32_t) * ntx * nty, cudaMemcpyDeviceToHost));
+    else std::memset(counts, 0, sizeof(uint32_t) * ntx * nty);
+  }
+  if (errors) {
+    if (live) CRT_CUDA(cudaMemcpy(errors, c->ad_err.p, sizeof(uint32_t) * ntx * nty, cudaMemcpyDeviceToHost));
+    else std::memset(errors, 0, sizeof(uint32_t) * ntx * nty);
+  }
   return CRT_OK;
 }
 

@@ -907,6 +907,44 @@ __device__ __forceinline__ void flush_counters(Counters* g, const Counters& c)
 
 // ------------------------------------------------------------------ kernels
 
+// GenerateRay: camera ray of one sample of pixel (px, py) into path slot `slot`.
+__device__ __forceinline__ void generate_path(const PathState& st, const DeviceParams& P, uint32_t slot, uint32_t px, uint32_t py,
+                                          uint32_t frame_seed)
+{
+  uint32_t rng = seed_rand(frame_seed, px, py, P.width, P.rng_radius);
+  const float jx = rand_float(rng);
+  const float jy = rand_float(rng);
+  float la = 0.0f, lb = 0.0f;
+  if (P.aperture_radius > 0.0f) { la = rand_float(rng); lb = rand_float(rng); }
+  const float fx = ((float)px + jx) / (float)P.width;
+  const float fy = ((float)py + jy) / (float)P.height;
+  const float sx = fmaf(fx, 2.0f, -1.0f) * P.hw;
+  const float sy = fmaf(fy, 2.0f, -1.0f) * P.hh;
+  const v3 eye = V(P.eye[0], P.eye[1], P.eye[2]);
+  const v3 cu = V(P.cu[0], P.cu[1], P.cu[2]), cv = V(P.cv[0], P.cv[1], P.cv[2]), cw = V(P.cw[0], P.cw[1], P.cw[2]);
+  v3 o, d;
+  if (P.is_ortho) {
+    o = vadd(eye, vadd(vscale(cu, sx), vscale(cv, sy)));
+    d = cw;
+  } else {
+    o = eye;
+    d = normalize3(vadd(cw, vadd(vscale(cu, sx), vscale(cv, sy))));
+  }
+  if (P.aperture_radius > 0.0f) {
+    const float ft = P.focal_dist / dot3(d, cw);
+    const v3 focus = vadd(o, vscale(d, ft));
+    float sn, cs;
+    sincos2pi(lb, sn, cs);
+    const float r = sqrtf(la) * P.aperture_radius;
+    o = vadd(o, vadd(vscale(cu, r * cs), vscale(cv, r * sn)));
+    d = normalize3(vsub(focus, o));
+  }
+  st_stream(&st.ray_o[slot], make_float4(o.x, o.y, o.z, 1.0f));
+  st_stream(&st.ray_d[slot], make_float4(d.x, d.y, d.z, __int_as_float(0)));
+  st_stream(&st.thr[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng)));
+  st_stream(&st.rad[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+}
+
 // GenerateRay for every path slot of the batch.  Slot layout: sample k
 // of the batch occupies slots [k*tiles*32, (k+1)*tiles*32); inside, each warp owns
 // an 8x4 pixel tile so primary rays of a warp are coherent.
@@ -925,40 +963,7 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
     const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
     const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
     const bool valid = slot < total && px < P.width && py < P.height;
-    if (valid) {
-      uint32_t rng = seed_rand(__ldg(frame_seeds + k), px, py, P.width, P.rng_radius);
-      const float jx = rand_float(rng);
-      const float jy = rand_float(rng);
-      float la = 0.0f, lb = 0.0f;
-      if (P.aperture_radius > 0.0f) { la = rand_float(rng); lb = rand_float(rng); }
-      const float fx = ((float)px + jx) / (float)P.width;
-      const float fy = ((float)py + jy) / (float)P.height;
-      const float sx = fmaf(fx, 2.0f, -1.0f) * P.hw;
-      const float sy = fmaf(fy, 2.0f, -1.0f) * P.hh;
-      const v3 eye = V(P.eye[0], P.eye[1], P.eye[2]);
-      const v3 cu = V(P.cu[0], P.cu[1], P.cu[2]), cv = V(P.cv[0], P.cv[1], P.cv[2]), cw = V(P.cw[0], P.cw[1], P.cw[2]);
-      v3 o, d;
-      if (P.is_ortho) {
-        o = vadd(eye, vadd(vscale(cu, sx), vscale(cv, sy)));
-        d = cw;
-      } else {
-        o = eye;
-        d = normalize3(vadd(cw, vadd(vscale(cu, sx), vscale(cv, sy))));
-      }
-      if (P.aperture_radius > 0.0f) {
-        const float ft = P.focal_dist / dot3(d, cw);
-        const v3 focus = vadd(o, vscale(d, ft));
-        float sn, cs;
-        sincos2pi(lb, sn, cs);
-        const float r = sqrtf(la) * P.aperture_radius;
-        o = vadd(o, vadd(vscale(cu, r * cs), vscale(cv, r * sn)));
-        d = normalize3(vsub(focus, o));
-      }
-      st_stream(&st.ray_o[slot], make_float4(o.x, o.y, o.z, 1.0f));
-      st_stream(&st.ray_d[slot], make_float4(d.x, d.y, d.z, __int_as_float(0)));
-      st_stream(&st.thr[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng)));
-      st_stream(&st.rad[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-    }
+    if (valid) generate_path(st, P, slot, px, py, __ldg(frame_seeds + k));
     if (aligned) {
       st.queue[0][slot] = slot;             // every slot is a pixel: identity queue, no atomics
     } else {
@@ -1297,6 +1302,201 @@ k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_b
   }
   if (gcnt && blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&gcnt->samples, (unsigned long long)P.width * P.height * n_batch);
+}
+
+// ------------------------------------------------------------------ adaptive screen sampling
+//
+// Graphic3d_RenderingParams::AdaptiveScreenSampling (SettingsWidget.cxx:427-478; OCCT's
+// OpenGl_TileSampler draws NbRayTracingTiles tiles per frame with probability proportional
+// to a per-tile error estimate).  Here the same expected distribution is dealt out by
+// systematic sampling in integer arithmetic, on the device, with no host round trip:
+//   wave budget B tile samples; tile weight w = clamp(err, W0/(8 NT), 4 W0/NT) + 1;
+//   cum[j] = floor((C_j * B + off) / Wt), C = exclusive prefix of w, off a Weyl offset < Wt;
+//   tile j receives k_j = cum[j+1] - cum[j] more samples for each of its pixels.
+// err[j] = sum over the tile's pixels of floor(4096 * |sqrt(min(L_all,1)) - sqrt(min(L_even,1))|),
+// the display-space distance between the mean of all samples and of the even-numbered ones.
+// Everything is integer or in a fixed float order, so the oracle's orc_render_adaptive
+// reproduces it bit for bit.
+
+constexpr uint32_t kAdaptiveTile = 32u;          // pixels per tile side (OCCT RayTracingTileSize)
+constexpr uint32_t kAdaptiveSlots = 1024u;       // path slots of one tile sample
+
+struct AdaptiveState {
+  uint32_t* count;      // samples per pixel of each tile so far
+  uint32_t* err;        // fixed-point error estimate per tile
+  uint32_t* cum;        // [nt + 1] exclusive prefix of this wave's tile samples
+  uint32_t* qoff;       // [nt + 1] exclusive prefix of this wave's paths (queue offsets)
+  float* even;          // per pixel: luminance sum of the even-numbered samples
+  uint32_t ntx, nty, nt;
+  uint32_t first_parity;  // parity of the first sample index of the accumulation
+};
+
+__device__ __forceinline__ uint32_t adaptive_valid(const AdaptiveState& A, const DeviceParams& P, uint32_t j, uint32_t& vw, uint32_t& vh)
+{
+  const uint32_t tx = j % A.ntx, ty = j / A.ntx;
+  vw = min(kAdaptiveTile, P.width - tx * kAdaptiveTile);
+  vh = min(kAdaptiveTile, P.height - ty * kAdaptiveTile);
+  return vw * vh;
+}
+
+// exclusive block scan of one 64-bit value per thread (1024 threads); returns the prefix, total in `total`
+__device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long v, unsigned long long* smem, unsigned long long& total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();                 // smem may still be read from a previous call
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = smem[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    smem[32 + lane] = w;           // inclusive scan of warp totals
+  }
+  __syncthreads();
+  total = smem[32 + 31];
+  const unsigned long long warp_base = warp ? smem[32 + warp - 1] : 0ull;
+  return warp_base + x - v;
+}
+
+// One CTA of 1024 threads; each thread owns a contiguous run of tiles.
+__global__ void __launch_bounds__(1024)
+k_adaptive_allocate(AdaptiveState A, DeviceParams P, uint32_t budget, uint32_t wave)
+{
+  __shared__ unsigned long long smem[64];
+  const uint32_t per = (A.nt + blockDim.x - 1) / blockDim.x;
+  const uint32_t j0 = min(threadIdx.x * per, A.nt), j1 = min(j0 + per, A.nt);
+  unsigned long long part = 0, W0 = 0, Wt = 0;
+  for (uint32_t j = j0; j < j1; ++j) part += A.err[j];
+  block_scan_u64(part, smem, W0);
+  const unsigned long long lo = W0 / (8ull * A.nt), hi = (4ull * W0) / A.nt;
+  part = 0;
+  for (uint32_t j = j0; j < j1; ++j) part += min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
+  unsigned long long C = block_scan_u64(part, smem, Wt);
+  const unsigned long long off = ((unsigned long long)((wave * 40503u) & 0xffffu) * Wt) >> 16;
+  // tile samples and paths of this thread's run
+  unsigned long long paths = 0;
+  {
+    unsigned long long c = C;
+    for (uint32_t j = j0; j < j1; ++j) {
+      const unsigned long long w = min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
+      const uint32_t a = (uint32_t)((c * budget + off) / Wt), b = (uint32_t)(((c + w) * budget + off) / Wt);
+      uint32_t vw, vh;
+      paths += (unsigned long long)(b - a) * adaptive_valid(A, P, j, vw, vh);
+      A.cum[j] = a;
+      c += w;
+    }
+  }
+  unsigned long long total_paths = 0;
+  unsigned long long q = block_scan_u64(paths, smem, total_paths);
+  {
+    unsigned long long c = C;
+    for (uint32_t j = j0; j < j1; ++j) {
+      const unsigned long long w = min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
+      const uint32_t a = (uint32_t)((c * budget + off) / Wt), b = (uint32_t)(((c + w) * budget + off) / Wt);
+      uint32_t vw, vh;
+      A.qoff[j] = (uint32_t)q;
+      q += (unsigned long long)(b - a) * adaptive_valid(A, P, j, vw, vh);
+      c += w;
+    }
+  }
+  if (threadIdx.x == 0) { A.cum[A.nt] = budget; A.qoff[A.nt] = (uint32_t)total_paths; }
+}
+
+// GenerateRay for the wave's tile samples.  Slot = tile sample * 1024 + (8x4 sub-tile * 32 + lane),
+// so a warp still owns an 8x4 pixel block; the queue is written at computed offsets (no atomics).
+__global__ void __launch_bounds__(256)
+k_generate_adaptive(PathState st, DeviceParams P, AdaptiveState A, const uint32_t* __restrict__ seeds, uint32_t budget)
+{
+  const uint32_t total = budget * kAdaptiveSlots;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += stride) {
+    const uint32_t ts = slot >> 10, within = slot & 1023u;
+    uint32_t lo = 0, hi = A.nt;                 // last j with cum[j] <= ts  (warp-uniform search)
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(A.cum + mid) <= ts) lo = mid; else hi = mid;
+    }
+    const uint32_t j = lo, t = ts - __ldg(A.cum + j);
+    const uint32_t sub = within >> 5, lane = within & 31u;
+    const uint32_t lx = (sub & 3u) * 8u + (lane & 7u), ly = (sub >> 2) * 4u + (lane >> 3);
+    uint32_t vw, vh;
+    const uint32_t nv = adaptive_valid(A, P, j, vw, vh);
+    if (lx < vw && ly < vh) {
+      const uint32_t px = (j % A.ntx) * kAdaptiveTile + lx, py = (j / A.ntx) * kAdaptiveTile + ly;
+      generate_path(st, P, slot, px, py, __ldg(seeds + __ldg(A.count + j) + t));
+      const uint32_t pos = (nv == kAdaptiveSlots) ? within : ly * vw + lx;
+      st.queue[0][__ldg(A.qoff + j) + t * nv + pos] = slot;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = A.qoff[A.nt];
+}
+
+__device__ __forceinline__ float luminance(float r, float g, float b)
+{
+  return fmaf(0.0722f, b, fmaf(0.7152f, g, 0.2126f * r));
+}
+
+// Accumulation of an adaptive wave: one CTA per tile, 4 pixels per thread; adds the tile's k new
+// samples of every pixel in sample order, refreshes the tile's error estimate and sample count.
+__global__ void __launch_bounds__(256)
+k_resolve_adaptive(PathState st, DeviceParams P, AdaptiveState A, float4* __restrict__ accum, Counters* gcnt)
+{
+  __shared__ uint32_t s_err[8];
+  for (uint32_t j = blockIdx.x; j < A.nt; j += gridDim.x) {
+    const uint32_t c0 = A.cum[j], k = A.cum[j + 1] - c0;
+    if (k == 0) continue;                        // block-uniform
+    const uint32_t n_old = A.count[j], n_new = n_old + k;
+    const uint32_t n_even = A.first_parity ? n_new / 2u : (n_new + 1u) / 2u;
+    uint32_t vw, vh;
+    const uint32_t nv = adaptive_valid(A, P, j, vw, vh);
+    uint32_t e_sum = 0;
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t q = threadIdx.x + 256u * i;
+      const uint32_t lx = q & 31u, ly = q >> 5;
+      if (lx >= vw || ly >= vh) continue;
+      const uint32_t within = ((ly >> 2) * 4u + (lx >> 3)) * 32u + (ly & 3u) * 8u + (lx & 7u);
+      const size_t pix = (size_t)((j / A.ntx) * kAdaptiveTile + ly) * P.width + (j % A.ntx) * kAdaptiveTile + lx;
+      float4 a = accum[pix];
+      float ev = A.even[pix];
+      for (uint32_t t = 0; t < k; ++t) {
+        const float4 c = ld_stream(&st.rad[(size_t)(c0 + t) * kAdaptiveSlots + within]);
+        const float r = (c.x != c.x) ? 0.0f : minf(c.x, P.max_radiance);
+        const float g = (c.y != c.y) ? 0.0f : minf(c.y, P.max_radiance);
+        const float b = (c.z != c.z) ? 0.0f : minf(c.z, P.max_radiance);
+        a.x += r; a.y += g; a.z += b; a.w += 1.0f;
+        if (((A.first_parity + n_old + t) & 1u) == 0u) ev += luminance(r, g, b);
+      }
+      accum[pix] = a;
+      A.even[pix] = ev;
+      if (n_new >= 2u && n_even > 0u) {
+        const float l_all = luminance(a.x, a.y, a.z) / (float)n_new;
+        const float l_even = ev / (float)n_even;
+        const float e = fabsf(sqrtf(minf(maxf(l_all, 0.0f), 1.0f)) - sqrtf(minf(maxf(l_even, 0.0f), 1.0f)));
+        e_sum += (uint32_t)(e * 4096.0f);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+    __syncthreads();                             // everyone has read count[j]; s_err free again
+    if ((threadIdx.x & 31u) == 0u) s_err[threadIdx.x >> 5] = e_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t e = 0;
+      for (int w = 0; w < 8; ++w) e += s_err[w];
+      A.err[j] = e;
+      A.count[j] = n_new;
+      if (gcnt) atomicAdd(&gcnt->samples, (unsigned long long)nv * k);
+    }
+  }
 }
 
 // Display.fs restated.

@@ -853,8 +853,12 @@ class DrawSession(Interp):
                 i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
             elif t in ("-rasterization", "-raster"):
                 raise TclError("rasterization is out of scope: only the path-traced mode is implemented")
-            elif t == "-iss":
-                i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)   # adaptive sampling: not implemented, ignored
+            elif t in ("-iss", "-adaptive"):      # CornellBox.tcl:78-79
+                p.AdaptiveScreenSampling = nxt.lower() not in ("off", "0"); i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
+            elif t in ("-nbtiles", "-tiles") and self._is_num(nxt):
+                p.NbRayTracingTiles = int(float(nxt)); i += 2
+            elif t == "-issd":                    # ShowSamplingTiles
+                p.ShowSamplingTiles = nxt.lower() not in ("off", "0"); i += 1 + (1 if nxt.lower() in ("on", "off", "0", "1") else 0)
             elif t in ("-maxrad", "-radianceclamping") and self._is_num(nxt):
                 p.RadianceClampingValue = float(nxt); i += 2
             elif t in ("-twoside", "-twosided"):

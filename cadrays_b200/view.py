@@ -152,7 +152,9 @@ class Graphic3d_RenderingParams:
     RadianceClampingValue: float = 50.0
     TwoSidedBsdfModels: bool = False
     CoherentPathTracingMode: bool = False
-    AdaptiveScreenSampling: bool = False        # not implemented
+    AdaptiveScreenSampling: bool = False        # SettingsWidget.cxx:70,427-436; vrenderparams -iss
+    NbRayTracingTiles: int = 256                # OCCT default 16*16; CADRays writes 64..1024 (SettingsWidget.cxx:72,471-476)
+    ShowSamplingTiles: bool = False             # debug view (SettingsWidget.cxx:443-449): V3d_View.SamplingTiles()
     ToneMappingMethod: int = Graphic3d_ToneMappingMethod_Disabled
     WhitePoint: float = 1.0
     Exposure: float = 0.0
@@ -170,8 +172,6 @@ class Graphic3d_RenderingParams:
         if self.Method != Graphic3d_RM_RAYTRACING or not self.IsGlobalIlluminationEnabled:
             raise ValueError("only Graphic3d_RM_RAYTRACING with IsGlobalIlluminationEnabled is implemented "
                              "(the path-traced mode CADRays calls 'GI', SettingsWidget.cxx:76-84)")
-        if self.AdaptiveScreenSampling:
-            raise ValueError("AdaptiveScreenSampling is not implemented")
         p = crt_params()
         p.max_depth = int(self.RaytracingDepth)
         p.max_radiance = float(self.RadianceClampingValue)
@@ -188,6 +188,8 @@ class Graphic3d_RenderingParams:
         p.background[:] = [float(v) for v in self.BackgroundColor]
         p.samples_per_batch = int(self.SamplesPerBatch)
         p.bvh_width = int(self.BvhWidth)
+        p.adaptive_sampling = int(self.AdaptiveScreenSampling)
+        p.adaptive_tiles = int(self.NbRayTracingTiles)
         return p
 
 
@@ -379,6 +381,17 @@ class V3d_View:
             img = out if out is not None else np.empty((h, w, 3), dtype=np.float32)
             check(self._lib.crt_read_hdr(self._ctx, _fptr(img), 0))
         return img
+
+    def SamplingTiles(self):
+        """Adaptive screen sampling state (what Graphic3d_RenderingParams::ShowSamplingTiles displays):
+        (samples per pixel, error estimate) of every 32x32 tile, each of shape (tiles_y, tiles_x)."""
+        tx, ty = C.c_uint32(), C.c_uint32()
+        check(self._lib.crt_adaptive_tiles_get(self._ctx, None, None, 0, C.byref(tx), C.byref(ty)))
+        n = tx.value * ty.value
+        counts, errs = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        u32 = C.POINTER(C.c_uint32)
+        check(self._lib.crt_adaptive_tiles_get(self._ctx, counts.ctypes.data_as(u32), errs.ctypes.data_as(u32), n, None, None))
+        return counts.reshape(ty.value, tx.value), errs.reshape(ty.value, tx.value)
 
     def AccumDevicePtr(self):
         p = C.c_void_p()

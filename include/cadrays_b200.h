@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CRT_ABI_VERSION 1
+#define CRT_ABI_VERSION 2
 
 typedef enum crt_status {
   CRT_OK               =  0,
@@ -112,6 +112,11 @@ typedef struct crt_params {
   int32_t  samples_per_batch;/* samples per pixel kept in flight per wave; 0 = auto */
   int32_t  bvh_width;        /* 0 or 2 = binary BVH (default); 4 = OCCT's optional QUAD_BVH collapse.
                                 Changing it rebuilds the scene at the next crt_commit. */
+  int32_t  adaptive_sampling;/* AdaptiveScreenSampling, SettingsWidget.cxx:70,427-436; `vrenderparams -iss`
+                                (CornellBox.tcl:78-79): 32x32-pixel screen tiles are sampled in proportion to
+                                their estimated visual error (see crt_render) */
+  int32_t  adaptive_tiles;   /* NbRayTracingTiles ("GPU load", SettingsWidget.cxx:72,471-476): tile samples one
+                                crt_render sample unit spends in adaptive mode; 0 = one per screen tile */
 } crt_params;
 
 /* Graphic3d_Camera as CADRays sets it (src/Launcher/AppViewer.cxx:947,993-1042;
@@ -225,6 +230,20 @@ int crt_commit(crt_context* ctx);
  * of batching, so disjoint sample ranges on several GPUs union to the
  * single-GPU stream set. */
 int crt_render(crt_context* ctx, uint32_t n_samples, uint64_t* out_total_samples);
+/* Adaptive screen sampling (crt_params.adaptive_sampling; OCCT's OpenGl_TileSampler driven by
+ * Graphic3d_RenderingParams::AdaptiveScreenSampling / NbRayTracingTiles, SettingsWidget.cxx:427-478).
+ * With it on, one crt_render sample unit spends `adaptive_tiles` tile samples (one tile sample =
+ * one more sample for every pixel of one 32x32 tile) instead of one sample for every pixel, and
+ * each wave hands them to the tiles in proportion to their error estimate, clamped to
+ * [1/8, 4] x the mean.  A pixel with n samples holds exactly the first n samples of its
+ * non-adaptive stream.  Per-pixel sample counts are in the accumulator's 4th channel;
+ * crt_adaptive_tiles_get copies the per-tile counts and error estimates (row-major tiles,
+ * CRT_ADAPTIVE_TILE pixels square; either array may be NULL) - what ShowSamplingTiles
+ * (SettingsWidget.cxx:443-449) displays.  Do not all-reduce a bound accumulator in place while
+ * adaptive sampling runs: the error estimate is kept from this context's own samples. */
+#define CRT_ADAPTIVE_TILE 32
+int crt_adaptive_tiles_get(crt_context* ctx, uint32_t* counts, uint32_t* errors, uint32_t capacity,
+                           uint32_t* out_tiles_x, uint32_t* out_tiles_y);
 /* As crt_render but returns after enqueueing on the context stream. */
 int crt_render_async(crt_context* ctx, uint32_t n_samples);
 int crt_sync(crt_context* ctx);

@@ -77,6 +77,8 @@ struct RenderingParams {
   float RadianceClampingValue = 50.f;
   bool TwoSidedBsdfModels = false, CoherentPathTracingMode = false, UseEnvironmentMapBackground = true;
   bool ToneMappingFilmic = false;
+  bool AdaptiveScreenSampling = false;   // SettingsWidget.cxx:70,427-436
+  int NbRayTracingTiles = 128;           // SettingsWidget.cxx:72 (CADRays' default)
   float WhitePoint = 1.f, Exposure = 0.f, CameraApertureRadius = 0.f, CameraFocalPlaneDist = 1.f;
   crt_params Record() const
   {
@@ -85,6 +87,7 @@ struct RenderingParams {
     p.coherent_rng = CoherentPathTracingMode; p.aperture_radius = CameraApertureRadius; p.focal_dist = CameraFocalPlaneDist;
     p.tone_map = ToneMappingFilmic; p.white_point = WhitePoint; p.exposure = Exposure;
     p.env_as_background = UseEnvironmentMapBackground;
+    p.adaptive_sampling = AdaptiveScreenSampling; p.adaptive_tiles = NbRayTracingTiles;
     return p;
   }
 };

@@ -1134,6 +1134,25 @@ static v3 path_trace(const orc_scene* s, v3 org, v3 dir, uint32_t* rng, crt_stat
   return radiance;
 }
 
+/* one sample of pixel (x, y): GenerateRay + PathTrace, then NaN -> 0 and the radiance clamp */
+static v3 render_sample(const orc_scene* s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t frame_seed,
+                        int radius, crt_stats* st)
+{
+  uint32_t rng = orc_seed_rand(frame_seed, x, y, w, radius);
+  float jx = orc_rand_float(&rng);
+  float jy = orc_rand_float(&rng);
+  float la = 0.0f, lb = 0.0f;
+  if (s->params.aperture_radius > 0.0f) { la = orc_rand_float(&rng); lb = orc_rand_float(&rng); }
+  float o[3], d[3];
+  orc_camera_ray(s, ((float)x + jx) / (float)w, ((float)y + jy) / (float)h, la, lb, o, d);
+  v3 c = path_trace(s, V(o[0], o[1], o[2]), V(d[0], d[1], d[2]), &rng, st);
+  float mr = s->params.max_radiance;
+  c.x = (c.x != c.x) ? 0.0f : minf(c.x, mr);
+  c.y = (c.y != c.y) ? 0.0f : minf(c.y, mr);
+  c.z = (c.z != c.z) ? 0.0f : minf(c.z, mr);
+  return c;
+}
+
 void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sample,
                 uint32_t n_samples, float* accum4, int nthreads, crt_stats* stats)
 {
@@ -1154,19 +1173,7 @@ void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sampl
 #pragma omp for schedule(dynamic, 4)
       for (int64_t y = 0; y < (int64_t)h; ++y) {
         for (uint32_t x = 0; x < w; ++x) {
-          uint32_t rng = orc_seed_rand(frame_seed, x, (uint32_t)y, w, radius);
-          float jx = orc_rand_float(&rng);
-          float jy = orc_rand_float(&rng);
-          float la = 0.0f, lb = 0.0f;
-          if (s->params.aperture_radius > 0.0f) { la = orc_rand_float(&rng); lb = orc_rand_float(&rng); }
-          float o[3], d[3];
-          orc_camera_ray(s, ((float)x + jx) / (float)w, ((float)y + jy) / (float)h, la, lb, o, d);
-          v3 c = path_trace(s, V(o[0], o[1], o[2]), V(d[0], d[1], d[2]), &rng, stats ? &local : NULL);
-          /* NaN -> 0, clamp to RadianceClampingValue, accumulate */
-          float mr = s->params.max_radiance;
-          c.x = (c.x != c.x) ? 0.0f : minf(c.x, mr);
-          c.y = (c.y != c.y) ? 0.0f : minf(c.y, mr);
-          c.z = (c.z != c.z) ? 0.0f : minf(c.z, mr);
+          v3 c = render_sample(s, x, (uint32_t)y, w, h, frame_seed, radius, stats ? &local : NULL);
           float* a = accum4 + 4 * ((size_t)y * w + x);
           a[0] += c.x; a[1] += c.y; a[2] += c.z; a[3] += 1.0f;
         }
@@ -1193,6 +1200,90 @@ void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sampl
       stats->samples += (uint64_t)w * h;
     }
   }
+}
+
+/* Adaptive screen sampling (Graphic3d_RenderingParams::AdaptiveScreenSampling, SettingsWidget.cxx:427-478),
+ * the specification the CUDA kernels k_adaptive_allocate / k_generate_adaptive / k_resolve_adaptive follow:
+ *   tiles of 32x32 pixels, NT of them; per wave a budget of B tile samples;
+ *   W0 = sum err;  w_j = min(max(err_j, W0 / (8 NT)), 4 W0 / NT) + 1;  C = exclusive prefix of w, Wt its total;
+ *   off = (((wave * 40503) & 0xffff) * Wt) >> 16;  cum_j = (C_j * B + off) / Wt;  k_j = cum_{j+1} - cum_j;
+ *   every pixel of tile j receives samples count_j .. count_j + k_j - 1 of its stream (added in that order);
+ *   even_p accumulates the luminance of the even-numbered samples;
+ *   err_j = sum_p floor(4096 * |sqrt(clamp01(L_all)) - sqrt(clamp01(L_even))|) for the tiles sampled in the wave.
+ * State (tile_count, tile_err: NT each; even: w*h; *wave) belongs to the caller and starts zeroed. */
+static float luminance(float r, float g, float b) { return fmaf(0.0722f, b, fmaf(0.7152f, g, 0.2126f * r)); }
+
+void orc_adaptive_allocate(const uint32_t* tile_err, uint32_t nt, uint32_t budget, uint32_t wave, uint32_t* cum)
+{
+  uint64_t W0 = 0, Wt = 0, C = 0;
+  for (uint32_t j = 0; j < nt; ++j) W0 += tile_err[j];
+  uint64_t lo = W0 / (8ull * nt), hi = (4ull * W0) / nt;
+  for (uint32_t j = 0; j < nt; ++j) {
+    uint64_t e = tile_err[j];
+    Wt += (e < lo ? lo : (e > hi ? hi : e)) + 1ull;
+  }
+  uint64_t off = ((uint64_t)((wave * 40503u) & 0xffffu) * Wt) >> 16;
+  for (uint32_t j = 0; j < nt; ++j) {
+    uint64_t e = tile_err[j];
+    cum[j] = (uint32_t)((C * budget + off) / Wt);
+    C += (e < lo ? lo : (e > hi ? hi : e)) + 1ull;
+  }
+  cum[nt] = budget;
+}
+
+void orc_render_adaptive(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sample, uint64_t tile_samples,
+                         uint64_t wave_cap, float* accum4, uint32_t* tile_count, uint32_t* tile_err, float* even,
+                         uint32_t* wave, int nthreads)
+{
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+  const uint32_t T = 32;
+  const uint32_t ntx = (w + T - 1) / T, nty = (h + T - 1) / T, nt = ntx * nty;
+  const int radius = s->params.coherent_rng ? 8 : 1;
+  const uint32_t parity = (uint32_t)(first_sample & 1u);
+  uint32_t* cum = (uint32_t*)malloc(sizeof(uint32_t) * (nt + 1));
+  while (tile_samples > 0) {
+    uint32_t budget = (uint32_t)(tile_samples < wave_cap ? tile_samples : wave_cap);
+    orc_adaptive_allocate(tile_err, nt, budget, *wave, cum);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t j = 0; j < (int64_t)nt; ++j) {
+      uint32_t k = cum[j + 1] - cum[j];
+      if (!k) continue;
+      uint32_t n_old = tile_count[j], n_new = n_old + k;
+      uint32_t n_even = parity ? n_new / 2u : (n_new + 1u) / 2u;
+      uint32_t x0 = ((uint32_t)j % ntx) * T, y0 = ((uint32_t)j / ntx) * T;
+      uint32_t e_sum = 0;
+      uint32_t* seeds = (uint32_t*)malloc(sizeof(uint32_t) * k);
+      for (uint32_t t = 0; t < k; ++t) seeds[t] = orc_bullard_frame_seed(s->params.frame_seed0, first_sample + n_old + t);
+      for (uint32_t y = y0; y < y0 + T && y < h; ++y) {
+        for (uint32_t x = x0; x < x0 + T && x < w; ++x) {
+          float* a = accum4 + 4 * ((size_t)y * w + x);
+          float ev = even[(size_t)y * w + x];
+          for (uint32_t t = 0; t < k; ++t) {
+            v3 c = render_sample(s, x, y, w, h, seeds[t], radius, NULL);
+            a[0] += c.x; a[1] += c.y; a[2] += c.z; a[3] += 1.0f;
+            if (((parity + n_old + t) & 1u) == 0u) ev += luminance(c.x, c.y, c.z);
+          }
+          even[(size_t)y * w + x] = ev;
+          if (n_new >= 2u && n_even > 0u) {
+            float l_all = luminance(a[0], a[1], a[2]) / (float)n_new;
+            float l_even = ev / (float)n_even;
+            float e = fabsf(sqrtf(minf(maxf(l_all, 0.0f), 1.0f)) - sqrtf(minf(maxf(l_even, 0.0f), 1.0f)));
+            e_sum += (uint32_t)(e * 4096.0f);
+          }
+        }
+      }
+      free(seeds);
+      tile_err[j] = e_sum;
+      tile_count[j] = n_new;
+    }
+    (*wave)++;
+    tile_samples -= budget;
+  }
+  free(cum);
 }
 
 /* Display.fs restated: mean * 2^exposure, optional filmic curve with

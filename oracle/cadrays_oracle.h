@@ -59,6 +59,13 @@ void orc_trace_events(const orc_scene* s, const float* org, const float* dir, co
  * nthreads <= 0: all OpenMP threads. */
 void orc_render(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sample,
                 uint32_t n_samples, float* accum4, int nthreads, crt_stats* stats);
+
+/* Adaptive screen sampling, the specification of the CUDA path's crt_params.adaptive_sampling (see the .c file).
+ * cum has nt + 1 entries. */
+void orc_adaptive_allocate(const uint32_t* tile_err, uint32_t nt, uint32_t budget, uint32_t wave, uint32_t* cum);
+void orc_render_adaptive(const orc_scene* s, uint32_t w, uint32_t h, uint64_t first_sample, uint64_t tile_samples,
+                         uint64_t wave_cap, float* accum4, uint32_t* tile_count, uint32_t* tile_err, float* even,
+                         uint32_t* wave, int nthreads);
 /* Display.fs restated: mean -> exposure -> optional filmic -> gamma 2 -> RGB8. */
 void orc_display(const orc_scene* s, const float* accum4, uint32_t w, uint32_t h, uint8_t* rgb8);
 void orc_hdr(const float* accum4, uint32_t w, uint32_t h, float* rgb32f);

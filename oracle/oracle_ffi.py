@@ -66,6 +66,10 @@ def lib() -> C.CDLL:
         L.orc_trace.argtypes = [C.c_void_p, _f, _f, _f, C.c_uint32, C.c_int, _i32, _i32, _f, _f, _f, C.POINTER(crt_stats)]
         L.orc_trace_brute.argtypes = [C.c_void_p, _f, _f, _f, C.c_uint32, C.c_int, _i32, _i32, _f, _f, _f]
         L.orc_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, _f, C.c_int, C.POINTER(crt_stats)]
+        _u32 = C.POINTER(C.c_uint32)
+        L.orc_adaptive_allocate.argtypes = [_u32, C.c_uint32, C.c_uint32, C.c_uint32, _u32]
+        L.orc_render_adaptive.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, _f,
+                                          _u32, _u32, _f, _u32, C.c_int]
         L.orc_display.argtypes = [C.c_void_p, _f, C.c_uint32, C.c_uint32, _u8]
         L.orc_hdr.argtypes = [_f, C.c_uint32, C.c_uint32, _f]
         L.orc_sincos2pi.argtypes = [C.c_float, _f, _f]
@@ -179,6 +183,19 @@ class OracleScene:
         self._L.orc_render(self._h, w, h, first_sample, n_samples, _fp(accum), nthreads, C.byref(st) if stats else None)
         return (accum, st.as_dict()) if stats else accum
 
+    def render_adaptive(self, w, h, tile_samples, wave_cap, state=None, first_sample=0, nthreads=0):
+        """Adaptive screen sampling (orc_render_adaptive).  `state` carries accum / tile counts / tile errors /
+        even-sample luminance / wave index between calls; returns it."""
+        nt = ((w + 31) // 32) * ((h + 31) // 32)
+        if state is None:
+            state = {"accum": np.zeros((h, w, 4), np.float32), "count": np.zeros(nt, np.uint32),
+                     "err": np.zeros(nt, np.uint32), "even": np.zeros((h, w), np.float32), "wave": C.c_uint32(0)}
+        _u32 = C.POINTER(C.c_uint32)
+        self._L.orc_render_adaptive(self._h, w, h, first_sample, tile_samples, wave_cap, _fp(state["accum"]),
+                                    state["count"].ctypes.data_as(_u32), state["err"].ctypes.data_as(_u32),
+                                    _fp(state["even"]), C.byref(state["wave"]), nthreads)
+        return state
+
     def display(self, accum):
         h, w = accum.shape[:2]
         out = np.empty((h, w, 3), dtype=np.uint8)
@@ -193,6 +210,15 @@ class OracleScene:
 
     def epsilon(self) -> float:
         return float(self._L.orc_scene_epsilon(self._h))
+
+
+def adaptive_allocate(tile_err, budget, wave):
+    """orc_adaptive_allocate: exclusive prefix (nt + 1 entries) of the tile samples a wave hands to each tile."""
+    err = np.ascontiguousarray(tile_err, dtype=np.uint32)
+    cum = np.zeros(err.size + 1, np.uint32)
+    _u32 = C.POINTER(C.c_uint32)
+    lib().orc_adaptive_allocate(err.ctypes.data_as(_u32), err.size, int(budget), int(wave), cum.ctypes.data_as(_u32))
+    return cum
 
 
 if __name__ == "__main__":

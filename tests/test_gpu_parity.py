@@ -469,3 +469,70 @@ def test_quad_bvh_parity(which, product_lib, oracle_lib):
     view.Update()
     assert not (np.frombuffer(view.ExportBVH(), np.uint32, 8)[7] & 2)
     view.Remove()
+
+
+# ------------------------------------------------------------------ adaptive screen sampling
+
+@pytest.mark.parametrize("tiles,size,batch", [(0, (128, 128), 3), (5, (112, 72), 2), (64, (101, 67), 1)])
+def test_adaptive_sampling_matches_oracle(tiles, size, batch, product_lib, oracle_lib):
+    """AdaptiveScreenSampling (SettingsWidget.cxx:427-478): the device-side tile scheduler deals out exactly the
+    tile samples the oracle's orc_render_adaptive does, over several waves, on ragged tile grids too."""
+    w, h = size
+    desc = scenes.cornell_box(w, h, depth=5, sphere_res=(24, 12))
+    p = desc.params
+    p.AdaptiveScreenSampling, p.NbRayTracingTiles, p.SamplesPerBatch = True, tiles, batch
+    view, orc = _pair(desc)
+    nt = ((w + 31) // 32) * ((h + 31) // 32)
+    per_unit = tiles if tiles else nt
+    t = _bound_accum(view)
+    state = None
+    for units in (4, 3):         # two calls: the state carries over; each is split into waves of batch * nt
+        view.Redraw(units)
+        state = orc.render_adaptive(w, h, units * per_unit, batch * nt, state)
+        counts, errs = view.SamplingTiles()
+        assert np.array_equal(counts.reshape(-1), state["count"])
+        assert np.array_equal(errs.reshape(-1), state["err"])
+        assert np.array_equal(t.cpu().numpy(), state["accum"])
+    assert int(state["count"].sum()) == 7 * per_unit
+    assert state["count"].max() > state["count"].min(), "the scheduler is expected to favour noisy tiles"
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB), orc.display(state["accum"]))
+    # switching it off restarts a plain accumulation
+    p.AdaptiveScreenSampling = False
+    view.SetRenderingParams(p)
+    view.Redraw(2)
+    assert np.array_equal(t.cpu().numpy(), orc.render(w, h, 2))
+    view.BindAccum(None)
+    view.Remove()
+
+
+def test_adaptive_sampling_full_size_prefix_property(product_lib):
+    """1080p C2: a pixel that received n samples adaptively holds exactly the sum of the first n samples of its
+    plain stream (bit-equal to a non-adaptive render of n spp), and the budget is spent exactly."""
+    desc = scenes.assembly()
+    p = desc.params
+    p.AdaptiveScreenSampling, p.NbRayTracingTiles, p.SamplesPerBatch = True, 0, 2
+    view = V3d_View(0)
+    desc.apply(view)
+    t = _bound_accum(view)
+    view.Redraw(6)               # 3 waves of 2 tile samples per tile on average
+    counts, errs = view.SamplingTiles()
+    assert int(counts.sum()) == 6 * counts.size
+    assert counts.max() > counts.min() and counts.min() >= 1
+    adaptive = t.cpu().numpy().copy()
+    per_pixel = np.repeat(np.repeat(counts, 32, axis=0), 32, axis=1)[:desc.height, :desc.width]
+    assert np.array_equal(adaptive[..., 3], per_pixel.astype(np.float32))
+    p.AdaptiveScreenSampling = False
+    view.SetRenderingParams(p)
+    values, freq = np.unique(counts, return_counts=True)
+    checked = 0
+    done = 0
+    for n in sorted(values[np.argsort(-freq)][:3]):   # the three most common sample counts
+        view.Redraw(int(n) - done)
+        done = int(n)
+        plain = t.cpu().numpy()
+        m = per_pixel == n
+        assert np.array_equal(adaptive[m], plain[m])
+        checked += int(m.sum())
+    assert checked > 100_000
+    view.BindAccum(None)
+    view.Remove()

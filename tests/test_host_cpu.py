@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol(product_lib):
     for name in sorted(declared):
         assert hasattr(product_lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_ffi.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert product_lib.crt_abi_version() == 1
+    version = int(re.search(r"#define CRT_ABI_VERSION (\d+)", header).group(1))
+    assert product_lib.crt_abi_version() == version == 2
 
 
 def test_struct_layouts_match_header():
@@ -33,7 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.crt_light) == 32
     assert C.sizeof(_ffi.crt_stats) == 112
     assert C.sizeof(_ffi.crt_camera) == 52
-    assert C.sizeof(_ffi.crt_params) == 68
+    assert C.sizeof(_ffi.crt_params) == 76
 
 
 def test_no_device_fails_loudly(product_lib):
@@ -202,8 +203,8 @@ def test_material_semantics_follow_cadrays():
     assert list(g.Kt)[:3] == [1, 1, 1] and g.FresnelCoat[0] == -3 and g.Absorption[3] == 6.0
     with pytest.raises(ValueError):
         Graphic3d_RenderingParams(IsGlobalIlluminationEnabled=False).to_c()
-    with pytest.raises(ValueError):
-        Graphic3d_RenderingParams(AdaptiveScreenSampling=True).to_c()
+    r = Graphic3d_RenderingParams(AdaptiveScreenSampling=True, NbRayTracingTiles=128).to_c()   # SettingsWidget.cxx:70-72
+    assert r.adaptive_sampling == 1 and r.adaptive_tiles == 128
 
 
 def test_scene_generators_are_seeded_and_sized():

@@ -469,3 +469,54 @@ def test_environment_orientation(product_lib, oracle_lib):
     phi = 2 * math.pi * (12.5 / 16) - math.pi
     c = look((math.cos(phi), math.sin(phi), 0.0), (0, 0, 1))
     assert c[1] > 0.8 and c[0] < 0.05 and c[2] < 0.05
+
+
+# ------------------------------------------------------------------ adaptive screen sampling
+
+def test_adaptive_allocation_properties(oracle_lib):
+    """The tile scheduler: spends the budget exactly, uniform without information, proportional to the error
+    estimate within the [1/8, 4] x mean clamp, bounded per tile, and rotates which tiles a small budget reaches."""
+    from oracle import oracle_ffi
+    g = np.random.default_rng(3)
+    for nt, budget in ((1, 7), (12, 5), (2040, 128), (2040, 16 * 2040), (8160, 3)):
+        err = (g.random(nt) ** 4 * 50000).astype(np.uint32)
+        for wave in (0, 1, 77):
+            cum = oracle_ffi.adaptive_allocate(err, budget, wave)
+            k = np.diff(cum.astype(np.int64))
+            assert cum[0] <= cum[1] and cum[-1] == budget and (k >= 0).all() and k.sum() == budget
+            assert k.max() <= 32 * budget // nt + 1
+    flat = np.diff(oracle_ffi.adaptive_allocate(np.zeros(100, np.uint32), 300, 5).astype(np.int64))
+    assert (flat == 3).all()
+    err = np.full(1000, 100, np.uint32)
+    err[:100] = 300                      # three times the error -> three times the samples
+    k = np.diff(oracle_ffi.adaptive_allocate(err, 120_000, 0).astype(np.int64))
+    assert abs(k[:100].mean() / k[100:].mean() - 3.0) < 0.05
+    err[:10] = 4_000_000                 # clamped at 4 x mean / floor at mean / 8
+    k = np.diff(oracle_ffi.adaptive_allocate(err, 120_000, 0).astype(np.int64))
+    assert k.max() <= 32 * (k.min() + 1) + 1 and k.max() > 16 * k.min()
+    seen = np.zeros(2040, bool)
+    for wave in range(40):               # 128 tiles per frame out of 2040: every tile is reached within a few frames
+        seen |= np.diff(oracle_ffi.adaptive_allocate(np.zeros(2040, np.uint32), 128, wave)) > 0
+    assert seen.all()
+
+
+def test_adaptive_render_is_a_prefix_of_the_plain_stream(oracle_lib):
+    """Every pixel that got n samples adaptively holds exactly the first n samples of its plain stream, summed in
+    the same order; noisy tiles (around the light, glass) get more than flat walls."""
+    desc = scenes.cornell_box(96, 80, depth=4, sphere_res=(16, 8))
+    o = _oracle(desc)
+    nt = 3 * 3
+    st = o.render_adaptive(96, 80, 6 * nt, 2 * nt)
+    assert st["wave"].value == 3 and int(st["count"].sum()) == 6 * nt
+    counts = st["count"].reshape(3, 3)
+    per_pixel = np.repeat(np.repeat(counts, 32, axis=0), 32, axis=1)[:80, :96]
+    assert np.array_equal(st["accum"][..., 3], per_pixel.astype(np.float32))
+    assert counts.max() > counts.min()
+    plain = np.zeros((80, 96, 4), np.float32)
+    done = 0
+    for n in np.unique(counts):
+        o.render(96, 80, int(n) - done, first_sample=done, accum=plain)
+        done = int(n)
+        m = per_pixel == n
+        assert np.array_equal(st["accum"][m], plain[m])
+    o.close()

@@ -235,3 +235,14 @@ def test_rttexture_binds_a_texture_with_scale(tmp_path):
     assert d.materials[d.instances[1][2]].to_c().Kd[3] == 0.0
     with pytest.raises(tcl.TclError):
         s.eval("rttexture M /no/such/file.png")
+
+
+def test_vrenderparams_adaptive_sampling_flags():
+    """`vrenderparams -iss` is the line CornellBox.tcl:78-79 suggests uncommenting; -nbtiles is NbRayTracingTiles."""
+    s = _load("vrenderparams -ray -gi -rayDepth 5\nvrenderparams -iss\n")
+    assert s.params.AdaptiveScreenSampling and s.params.RaytracingDepth == 5
+    s = _load("vrenderparams -iss on -nbtiles 512 -rayDepth 3")
+    assert s.params.AdaptiveScreenSampling and s.params.NbRayTracingTiles == 512 and s.params.RaytracingDepth == 3
+    assert s.params.to_c().adaptive_tiles == 512
+    s = _load("vrenderparams -iss off")
+    assert not s.params.AdaptiveScreenSampling
