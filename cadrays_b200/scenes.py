@@ -382,6 +382,33 @@ def materials_scene(width=1920, height=1080, depth=12, sphere_res=(128, 64), env
     return s
 
 
+def synthetic_env(width=2048, height=1024) -> np.ndarray:
+    """Procedural lat-long sky of the shape of data/maps/default.jpg (2048x1024; the JPEG itself is the
+    reference's data and is not shipped): horizon-to-zenith gradient, a warm sun with a halo, dark ground.
+    Float radiance, deterministic."""
+    v = (np.arange(height, dtype=np.float32) + 0.5) / height          # 0 = up
+    u = (np.arange(width, dtype=np.float32) + 0.5) / width
+    el = (0.5 - v)[:, None] * np.float32(np.pi)                        # elevation
+    az = (u[None, :] - 0.5) * np.float32(2 * np.pi)
+    up = np.clip(np.sin(el), 0, 1)
+    sky = np.stack([0.35 + 0.25 * (1 - up), 0.50 + 0.20 * (1 - up), 0.85 - 0.15 * (1 - up)], axis=-1) * (0.6 + 0.6 * up[..., None])
+    sky = np.broadcast_to(sky, (height, width, 3)).copy()
+    ground = np.array([0.18, 0.16, 0.14], np.float32)
+    img = np.where((el > 0)[..., None], sky, ground[None, None, :]).astype(np.float32)
+    sun_el, sun_az = np.float32(0.75), np.float32(-0.9)
+    d = np.sin(el) * np.sin(sun_el) + np.cos(el) * np.cos(sun_el) * np.cos(az - sun_az)
+    ang = np.arccos(np.clip(d, -1, 1))
+    img += (np.exp(-(ang / 0.035) ** 2) * 60.0 + np.exp(-(ang / 0.25) ** 2) * 0.8)[..., None] * np.array([1.0, 0.93, 0.8], np.float32)
+    return np.ascontiguousarray(img, dtype=np.float32)
+
+
+def product_shot(width=3840, height=2160, depth=12, sphere_res=(128, 64)) -> SceneDesc:
+    """Config C4: the Materials.tcl geometry lit only by a 2048x1024 environment map, 3840x2160."""
+    s = materials_scene(width, height, depth, sphere_res, env=synthetic_env())
+    s.name = "product_shot"
+    return s
+
+
 # ------------------------------------------------------------------ C5: instanced stress
 
 def instanced(n_inst=1024, n_meshes=16, seed=5, width=1920, height=1080, depth=8, nu=80, nv=65) -> SceneDesc:
