@@ -58,6 +58,8 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+constexpr size_t kCounterWords = 4 * 64 + 8;   // queue lengths and work counters of one (half-)wave
+
 enum Family { F_GENERATE = 0, F_EXTEND, F_SHADE, F_CONNECT, F_RESOLVE, F_RENDER, F_COUNT };
 
 struct TimedSpan { int family; cudaEvent_t a, b; };
@@ -128,6 +130,12 @@ struct crt_context {
   bool persistent = true;
   bool fuse_traversal = true;   // connect(d) + extend(d+1) in one launch (CRT_FUSE=0 disables)
   bool l2_persist = false;      // L2 access-policy window over the scene arena (CRT_L2_PERSIST=1)
+  // software pipeline: a wave is split into two half-waves on two streams so that the latency-bound shading of
+  // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
+  bool pipeline = false;
+  int pipeline_trace_ctas = 5;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // metrics
   DevBuf<Counters> d_counters;
@@ -178,14 +186,14 @@ cudaEvent_t get_event(crt_context* c)
 }
 
 struct SpanGuard {
-  crt_context* c; int family; cudaEvent_t a = nullptr;
-  SpanGuard(crt_context* c_, int f) : c(c_), family(f)
+  crt_context* c; int family; cudaStream_t s; cudaEvent_t a = nullptr;
+  SpanGuard(crt_context* c_, int f, cudaStream_t s_ = nullptr) : c(c_), family(f), s(s_ ? s_ : c_->stream)
   {
-    if (c->timing_on) { a = get_event(c); cudaEventRecord(a, c->stream); }
+    if (c->timing_on) { a = get_event(c); cudaEventRecord(a, s); }
   }
   ~SpanGuard()
   {
-    if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({ family, a, b }); }
+    if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, s); c->spans.push_back({ family, a, b }); }
   }
 };
 
@@ -378,56 +386,92 @@ int resident_grid(const crt_context* c, K kernel, int block)
   return c->sm_count * per_sm;
 }
 
-// One wave: n_batch samples of every pixel, or (adaptive != nullptr) `n_batch` tile samples dealt out by
-// k_adaptive_allocate.
-template <bool COUNT, bool QUAD>
-int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, const AdaptiveState* adaptive = nullptr)
+PathState make_state(crt_context* c, size_t slot0, int half)
 {
   PathState st;
-  st.ray_o = c->ray_o.p; st.ray_d = c->ray_d.p; st.thr = c->thr.p; st.rad = c->rad.p;
-  st.hit = c->hit.p; st.hit_inst = c->hit_inst.p;
-  st.queue[0] = c->queue0.p; st.queue[1] = c->queue1.p;
-  st.sh_o = c->sh_o.p; st.sh_d = c->sh_d.p; st.sh_c = c->sh_c.p;
+  st.ray_o = c->ray_o.p + slot0; st.ray_d = c->ray_d.p + slot0; st.thr = c->thr.p + slot0; st.rad = c->rad.p + slot0;
+  st.hit = c->hit.p + slot0; st.hit_inst = c->hit_inst.p + slot0;
+  st.queue[0] = c->queue0.p + slot0; st.queue[1] = c->queue1.p + slot0;
+  st.sh_o = c->sh_o.p + slot0; st.sh_d = c->sh_d.p + slot0; st.sh_c = c->sh_c.p + slot0;
   const int depth_max = c->dp.max_depth;
-  st.n_active = c->counters.p;
-  st.n_shadow = c->counters.p + (depth_max + 1);
+  st.n_active = c->counters.p + (size_t)half * kCounterWords;
+  st.n_shadow = st.n_active + (depth_max + 1);
   st.work_extend = st.n_shadow + depth_max;
   st.work_connect = st.work_extend + depth_max;
+  return st;
+}
+
+// generate + all bounces of one (half-)wave on stream s; path state indices are relative to st
+template <bool COUNT, bool QUAD>
+int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_t n_batch, const uint32_t* d_seeds,
+                    const AdaptiveState* adaptive, int trace_ctas)
+{
+  const int depth_max = c->dp.max_depth;
   Counters* gc = c->d_counters.p;
-  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * (4 * depth_max + 2), c->stream));
   const bool pers = c->persistent || QUAD;      // the 4-wide walk exists in the persistent driver only
   const bool fuse = pers && c->fuse_traversal;
-  static const int g_ext = resident_grid(c, k_extend<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
-  static const int g_con = resident_grid(c, k_connect<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
-  static const int g_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  static const int r_ext = resident_grid(c, k_extend<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int r_con = resident_grid(c, k_connect<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int r_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  const int cap = trace_ctas > 0 ? c->sm_count * trace_ctas : (1 << 30);
+  const int g_ext = std::min(r_ext, cap), g_con = std::min(r_con, cap), g_dual = std::min(r_dual, cap);
   {
-    SpanGuard g(c, F_GENERATE);
-    if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, d_seeds, n_batch);
-    else k_generate<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, d_seeds, n_batch);
+    SpanGuard g(c, F_GENERATE, s);
+    if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, *adaptive, d_seeds, n_batch);
+    else k_generate<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, d_seeds, n_batch);
   }
   for (int depth = 0; depth < depth_max; ++depth) {
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
-      SpanGuard g(c, F_EXTEND);
-      if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      SpanGuard g(c, F_EXTEND, s);
+      if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
     }
     {
-      SpanGuard g(c, F_SHADE);
-      if (c->ds.n_tex) k_shade<COUNT, true><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
-      else k_shade<COUNT, false><<<grid_for(c, 8), 128, 0, c->stream>>>(c->ds, c->dp, st, depth, gc);
+      SpanGuard g(c, F_SHADE, s);
+      if (c->ds.n_tex) k_shade<COUNT, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc);
+      else k_shade<COUNT, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc);
     }
     if (!fuse || depth == depth_max - 1) {
-      SpanGuard g(c, F_CONNECT);
-      if (pers) k_connect<COUNT, true, QUAD><<<g_con, CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
-      else k_connect<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, c->stream>>>(c->ds, st, depth, gc);
+      SpanGuard g(c, F_CONNECT, s);
+      if (pers) k_connect<COUNT, true, QUAD><<<g_con, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      else k_connect<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
     }
   }
-  {
+  return CRT_OK;
+}
+
+// One wave: n_batch samples of every pixel, or (adaptive != nullptr) `n_batch` tile samples dealt out by
+// k_adaptive_allocate.  Pipelined form: the wave is split into two half-waves that run on two streams, so the
+// shading kernels of one half (latency / HBM bound) share the SMs with the traversal kernels of the other
+// (L1 / ALU bound); the halves are accumulated in sample order, so the result does not change.
+template <bool COUNT, bool QUAD>
+int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, const AdaptiveState* adaptive = nullptr)
+{
+  const int depth_max = c->dp.max_depth;
+  Counters* gc = c->d_counters.p;
+  const bool split = c->pipeline && !adaptive && n_batch >= 2 && c->stream2;
+  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * ((split ? kCounterWords : 0) + 4 * depth_max + 2), c->stream));
+  if (!split) {
+    const PathState st = make_state(c, 0, 0);
+    enqueue_bounces<COUNT, QUAD>(c, st, c->stream, n_batch, d_seeds, adaptive, 0);
     SpanGuard g(c, F_RESOLVE);
     if (adaptive) k_resolve_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, c->accum, COUNT ? gc : nullptr);
     else k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
+  } else {
+    const uint32_t n_a = (n_batch + 1) / 2, n_b = n_batch - n_a;
+    const size_t per_sample = (size_t)c->dp.tiles_x * c->dp.tiles_y * 32u;
+    const PathState st_a = make_state(c, 0, 0), st_b = make_state(c, per_sample * n_a, 1);
+    CRT_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    CRT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    enqueue_bounces<COUNT, QUAD>(c, st_a, c->stream, n_a, d_seeds, nullptr, c->pipeline_trace_ctas);
+    enqueue_bounces<COUNT, QUAD>(c, st_b, c->stream2, n_b, d_seeds + n_a, nullptr, c->pipeline_trace_ctas);
+    CRT_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    SpanGuard g(c, F_RESOLVE);
+    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st_a, c->dp, c->accum, n_a, COUNT ? gc : nullptr);
+    CRT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st_b, c->dp, c->accum, n_b, COUNT ? gc : nullptr);
   }
   CRT_CUDA(cudaGetLastError());
   return CRT_OK;
@@ -499,7 +543,7 @@ int render_impl(crt_context* c, uint32_t n_samples)
   if ((rc = upload_tables(c))) return rc;
   update_device_params(c);
   if (n_samples == 0) return CRT_OK;
-  CRT_CUDA(c->counters.ensure(4 * 64 + 8));
+  CRT_CUDA(c->counters.ensure(2 * kCounterWords));
   if (c->params.adaptive_sampling) return render_adaptive(c, n_samples);
   const uint32_t batch = std::min(auto_batch(c), n_samples);
   if ((rc = ensure_path_state(c, batch))) return rc;
@@ -581,12 +625,17 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(1, std::atoi(tv));
 
   crt_params_default(&c->params);
   std::memset(&c->cam, 0, sizeof c->cam);
   c->cam.dir[1] = 1.0f; c->cam.up[2] = 1.0f; c->cam.fovy_deg = 45.0f; c->cam.aspect = 1.0f; c->cam.ortho_scale = 1.0f;
   cudaError_t se = cudaSetDevice(device_ordinal);
   if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (se == cudaSuccess) se = c->d_counters.ensure(1);
   if (se == cudaSuccess) se = cudaMemset(c->d_counters.p, 0, sizeof(Counters));
   if (se != cudaSuccess) {
@@ -625,6 +674,9 @@ void crt_destroy(crt_context* c)
   c->queue0.release(); c->queue1.release(); c->counters.release(); c->seeds.release();
   c->accum_internal.release(); c->d_ldr.release(); c->d_hdr.release(); c->d_counters.release();
   c->ad_count.release(); c->ad_err.release(); c->ad_cum.release(); c->ad_qoff.release(); c->ad_seeds.release(); c->ad_even.release();
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
