@@ -26,22 +26,62 @@ def write_png(path: str, rgb8_bottom_up: np.ndarray) -> None:
 
 
 def read_png_rgb8(path: str) -> np.ndarray:
-    """Minimal reader for files written by write_png (8-bit RGB, filter 0); returns top-down rows."""
+    """Reader for 8-bit, non-interlaced RGB / RGBA / grey PNG files (all five scanline filters): what write_png
+    produces and what `rttexture` / the material icons of the reference use.  Returns top-down rows, RGB."""
     data = open(path, "rb").read()
-    assert data[:8] == b"\x89PNG\r\n\x1a\n"
-    pos, idat, w, h = 8, b"", 0, 0
+    if data[:8] != b"\x89PNG\r\n\x1a\n":
+        raise ValueError(f"{path}: not a PNG file")
+    pos, idat, w, h, depth, ctype, interlace = 8, b"", 0, 0, 8, 2, 0
+    palette = None
     while pos < len(data):
         n, tag = struct.unpack(">I4s", data[pos:pos + 8])
         body = data[pos + 8:pos + 8 + n]
         if tag == b"IHDR":
-            w, h = struct.unpack(">II", body[:8])
+            w, h, depth, ctype, _, _, interlace = struct.unpack(">IIBBBBB", body[:13])
+        elif tag == b"PLTE":
+            palette = np.frombuffer(body, dtype=np.uint8).reshape(-1, 3)
         elif tag == b"IDAT":
             idat += body
         pos += 12 + n
-    raw = zlib.decompress(idat)
-    rows = np.frombuffer(raw, dtype=np.uint8).reshape(h, 1 + 3 * w)
-    assert (rows[:, 0] == 0).all()
-    return rows[:, 1:].reshape(h, w, 3).copy()
+    channels = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}.get(ctype)
+    if depth != 8 or interlace != 0 or channels is None:
+        raise ValueError(f"{path}: only 8-bit non-interlaced PNG files are supported")
+    stride = w * channels
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + stride)
+    out = np.zeros((h, stride), dtype=np.uint8)
+    prev = np.zeros(stride, dtype=np.int32)
+    for y in range(h):
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + prev) & 255
+        else:
+            cur = np.zeros(stride, dtype=np.int32)
+            for x in range(stride):
+                a = cur[x - channels] if x >= channels else 0
+                b = prev[x]
+                c = prev[x - channels] if x >= channels else 0
+                if f == 1:
+                    pred = a
+                elif f == 3:
+                    pred = (a + b) >> 1
+                elif f == 4:
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                else:
+                    raise ValueError(f"{path}: bad scanline filter {f}")
+                cur[x] = (line[x] + pred) & 255
+        out[y] = cur
+        prev = cur
+    px = out.reshape(h, w, channels)
+    if ctype == 3:
+        if palette is None:
+            raise ValueError(f"{path}: palette image without PLTE")
+        return palette[px[..., 0]].copy()
+    if channels == 1 or channels == 2:
+        return np.repeat(px[..., :1], 3, axis=2).copy()
+    return px[..., :3].copy()
 
 
 def write_hdr(path: str, rgb32f_bottom_up: np.ndarray) -> None:

@@ -48,6 +48,16 @@ def _plastic(kd, rough=0.1):
     return lambda: Graphic3d_BSDF(Kd=list(kd), Ks=[0.04, 0.04, 0.04, rough], FresnelBase=Graphic3d_Fresnel.CreateConstant(1.0))
 
 
+# Values: what the reference itself reveals, in this order of trust --
+#   (1) BSDFs the shipped scripts export right after `vsetmaterial X` (Materials.tcl:40-190: Brass Schlick colour,
+#       Glass absorption 0.75 0.95 0.9 / 0.05 with a 1.62 dielectric, Aluminium Schlick colour and roughness);
+#   (2) the 64x64 icons data/materials/<MaterialName>.png, which are OCCT path-traced renders of
+#       data/other/preview.tcl for every named material: the ball's colour relative to the plaster ball calibrates
+#       albedo and tint here (tests/golden/material_icons.json, tests/test_tcl_cpu.py);
+#   (3) recalled Graphic3d_MaterialAspect.cxx values where neither exists.
+# The icons also settle which name is which: files are named Graphic3d_MaterialAspect::MaterialName(id)
+# (main.cxx:120-132), in enum order "... Metalized, Ionized, Chrome, Aluminium, Obsidian, Neon, Jade ...", so
+# NEON_GNC is the grey "Ionized" and NEON_PHC the green emissive "Neon".
 NAMED_MATERIALS: Dict[str, Callable[[], Graphic3d_BSDF]] = {
     "brass": _metal((0.58, 0.42, 0.20), 0.045),            # Schlick colour as used with Brass in Materials.tcl:49
     "bronze": _metal((0.65, 0.35, 0.15), 0.045),
@@ -59,21 +69,27 @@ NAMED_MATERIALS: Dict[str, Callable[[], Graphic3d_BSDF]] = {
     "chrome": _metal((0.549, 0.556, 0.554), 0.02),
     "aluminium": _metal((0.913183, 0.921494, 0.924524), 0.026),   # Materials.tcl:159-171
     "aluminum": _metal((0.913183, 0.921494, 0.924524), 0.026),
+    "metalized": _metal((0.28, 0.28, 0.26), 0.2),
     "plaster": _diffuse((0.482353, 0.482353, 0.482353)),
     "plastic": _plastic((0.2, 0.2, 0.2)),
-    "shiny_plastic": _plastic((0.2, 0.2, 0.2), 0.02),
-    "satin": _plastic((0.3, 0.3, 0.3), 0.3),
-    "stone": _diffuse((0.5, 0.45, 0.4)),
-    "charcoal": _diffuse((0.05, 0.05, 0.05)),
-    "obsidian": _plastic((0.05, 0.05, 0.07), 0.02),
-    "jade": _plastic((0.3, 0.6, 0.4), 0.1),
-    "neon_gnc": lambda: Graphic3d_BSDF(Kd=[0.1, 0.1, 0.1], Le=[0.0, 1.0, 0.46]),
-    "neon_phc": lambda: Graphic3d_BSDF(Kd=[0.1, 0.1, 0.1], Le=[1.0, 1.0, 1.0]),
-    "glass": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (1, 1, 1), 0.0, 1.5),
-    "water": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (0.8, 0.9, 1.0), 0.1, 1.33),
+    "shiny_plastic": _plastic((0.3, 0.3, 0.3), 0.02),
+    "satin": _plastic((0.62, 0.62, 0.62), 0.3),
+    "stone": _diffuse((0.25, 0.245, 0.24)),
+    "charcoal": _plastic((0.08, 0.08, 0.08), 0.3),
+    "obsidian": _plastic((0.03, 0.01, 0.027), 0.02),
+    "jade": _plastic((0.23, 0.43, 0.23), 0.1),
+    "neon_gnc": _plastic((0.28, 0.28, 0.28), 0.1),                                   # "Ionized"
+    "neon_phc": lambda: Graphic3d_BSDF(Kd=[0.1, 0.1, 0.1], Le=[0.0, 1.0, 0.46]),     # "Neon"
+    "glass": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (0.75, 0.95, 0.9), 0.05, 1.62),   # Materials.tcl:74-88
+    "water": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (0.8, 0.9, 1.0), 0.05, 1.33),
     "diamond": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (1, 1, 1), 0.0, 2.42),
+    "transparent": lambda: Graphic3d_BSDF.CreateGlass((1, 1, 1), (1, 1, 1), 0.0, 1.0),
     "default": _plastic((0.6, 0.6, 0.6)),
 }
+# Graphic3d_MaterialAspect::MaterialName() spellings (the GUI's and the icon files' names)
+for _alias, _name in (("plastered", "plaster"), ("plastified", "plastic"), ("shiny_plastified", "shiny_plastic"),
+                      ("satined", "satin"), ("ionized", "neon_gnc"), ("neon", "neon_phc")):
+    NAMED_MATERIALS[_alias] = NAMED_MATERIALS[_name]
 
 
 # ------------------------------------------------------------------ a small Tcl evaluator
@@ -229,9 +245,13 @@ class Interp:
                     k = s.index("}", j)
                     name, j = s[j + 1:k], k + 1
                 else:
+                    if s.startswith("::", j):          # $::name: the global namespace, the only one here
+                        j += 2
                     while j < n and (s[j].isalnum() or s[j] == "_"):
                         j += 1
                     name = s[i + 1:j]
+                if name.startswith("::"):
+                    name = name[2:]
                 if not name:
                     out.append("$")
                     i += 1
@@ -465,7 +485,12 @@ class DrawSession(Interp):
         self.width, self.height = width, height
         self.shapes: Dict[str, _Shape] = {}
         self.objects: Dict[str, _Object] = {}     # displayed AIS objects, insertion ordered
-        self.lights: List[dict] = [dict(kind="directional", head=True, vec=(0, 0, -1), smooth=0.0, intensity=1.0, color=(1, 1, 1))]
+        # V3d_Viewer::SetDefaultLights(): a directional head light (0) and an ambient light (1, no path-traced effect)
+        self.lights: List[dict] = [dict(kind="directional", head=True, vec=(0, 0, -1), smooth=0.0, intensity=1.0, color=(1, 1, 1)),
+                                   dict(kind="ambient", head=False, vec=(0, 0, 0), smooth=0.0, intensity=1.0, color=(1, 1, 1))]
+        self.size_fixed = False                    # True: `vinit w= h=` does not change the size the caller chose
+        self.on_dump: Optional[Callable] = None    # on_dump(session, path, frames) renders a `vdump`
+        self.dumps: List[tuple] = []               # (path, frames, SceneDesc) of every `vdump` when on_dump is None
         self.params = Graphic3d_RenderingParams()
         self.proj = np.array([0.0, -1.0, 0.0])     # direction from the scene towards the eye
         self.up = np.array([0.0, 0.0, 1.0])
@@ -485,7 +510,7 @@ class DrawSession(Interp):
         for name in ("box psphere pcylinder compound explode ttranslate trotate tcopy vclear vdisplay verase vremove vlocation "
                      "vsetmaterial vbsdf vlight rtlight vcamera vviewparams vfront vback vtop vbottom vleft vright vaxo vfit "
                      "vrenderparams vtextureenv vsetdispmode vinit vfps vdump pload vglinfo vzbufftrihedron vrepaint vupdate "
-                     "rtmeshread rtdisplay rterase rttexture vtexture").split():
+                     "rtmeshread rtdisplay rterase rttexture vtexture vvbo incmesh vsetlocation").split():
             self.cmds[name] = getattr(self, "_d_" + name, self._d_ignore)
 
     def _d_ignore(self, a):
@@ -887,14 +912,46 @@ class DrawSession(Interp):
             self.envmap = None
             return
         path = a[-1]
-        from PIL import Image
         if not os.path.exists(path):
-            raise TclError(f"vtextureenv: cannot read '{path}'")
+            # OCCT reports the unreadable file and goes on without a map (preview.tcl:56 names a file of its author's disk)
+            self.output.append(f"vtextureenv: cannot read '{path}', no environment map")
+            self.envmap = None
+            return
+        from PIL import Image
         self.envmap = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
 
     def _d_vfps(self, a):
         if a and self._is_num(a[0]):
             self.frames = int(float(a[0]))
+
+    def _d_vinit(self, a):
+        """`vinit name=View1 w=128 h=128` (data/other/preview.tcl:10): the window size, unless the caller fixed one."""
+        for t in a:
+            k, _, v = t.partition("=")
+            k = k.lower().lstrip("-")
+            if k in ("w", "width") and v.isdigit() and not self.size_fixed:
+                self.width = int(v)
+            elif k in ("h", "height") and v.isdigit() and not self.size_fixed:
+                self.height = int(v)
+
+    def _d_vsetlocation(self, a):
+        """`vsetlocation [-noupdate] name x y z` (data/other/preview.tcl:23): translation of the object."""
+        names = [t for t in a if not t.startswith("-") or self._is_num(t)]
+        if len(names) != 4:
+            raise TclError("vsetlocation name x y z")
+        self._obj(names[0]).location[:, 3] = [float(v) for v in names[1:]]
+
+    def _d_vdump(self, a):
+        """`vfps N` + `vdump file` is how preview.tcl renders one icon per material (:62-65): each vdump hands the
+        current scene and frame count to `on_dump` (a renderer), or records them in `dumps`."""
+        paths = [t for t in a if not t.startswith("-")]
+        if not paths:
+            raise TclError("vdump file")
+        if self.on_dump is not None:
+            self.on_dump(self, paths[0], self.frames)
+        else:
+            import copy
+            self.dumps.append((paths[0], self.frames, copy.deepcopy(self.scene())))
 
     # -- result
     def scene(self) -> scenes.SceneDesc:

@@ -246,3 +246,81 @@ def test_vrenderparams_adaptive_sampling_flags():
     assert s.params.to_c().adaptive_tiles == 512
     s = _load("vrenderparams -iss off")
     assert not s.params.AdaptiveScreenSampling
+
+
+# ------------------------------------------------------------------ data/other/preview.tcl and the material icons
+
+ICON_OF = {"plaster": "plastered", "plastic": "plastified", "shiny_plastic": "shiny_plastified", "satin": "satined",
+           "neon_gnc": "ionized", "neon_phc": "neon"}     # Graphic3d_MaterialAspect::MaterialName() spellings
+
+
+def _preview_session(size=64):
+    s = tcl.DrawSession(size, size, root=str(REF_SCRIPTS.parent / "other"))
+    s.size_fixed = True
+    s.strict = True
+    with open(REF_SCRIPTS.parent / "other" / "preview.tcl", encoding="utf-8", errors="replace") as f:
+        s.eval(f.read())
+    return s
+
+
+@pytest.mark.skipif(not REF_SCRIPTS.exists(), reason="reference tree not mounted (GPU box)")
+def test_preview_script_runs_unchanged():
+    """data/other/preview.tcl (the script that rendered data/materials/*.png) evaluates with no unknown command:
+    `vinit w= h=`, `vsetlocation`, `vlight del 1` on the default ambient light, a missing environment file,
+    `foreach` over $::THE_MATERIALS with `vfps 8000` + `vdump` per material."""
+    s = tcl.load_script(str(REF_SCRIPTS.parent / "other" / "preview.tcl"), strict=True)
+    assert (s.width, s.height) == (128, 128)                      # vinit w=128 h=128
+    assert len(s.dumps) == 24 and all(fr == 8000 for _, fr, _ in s.dumps)
+    assert any("cannot read" in line for line in s.output)
+    names = [os.path.splitext(os.path.basename(p))[0] for p, _, _ in s.dumps]
+    assert names[:4] == ["brass", "bronze", "copper", "gold"] and names[-1] == "transparent"
+    for _, _, d in s.dumps:
+        assert len(d.instances) == 145 and len(d.lights) == 1 and d.envmap is None
+        assert d.params.RaytracingDepth == 10 and d.lights[0].is_point == 0
+        assert 0.0 < d.lights[0].smoothness < 1.0                 # cone of `vlight change 0 sm 0.3`
+    ball = {n: d.materials[d.instances[0][2]] for n, (_, _, d) in zip(names, s.dumps)}
+    assert ball["neon_phc"].Le[1] > 0.5 and sum(ball["neon_gnc"].Le) == 0       # "Neon" glows, "Ionized" does not
+    assert ball["glass"].Absorption == [0.75, 0.95, 0.9, 0.05]                  # Materials.tcl:74-88
+
+
+@pytest.mark.skipif(not REF_SCRIPTS.exists(), reason="reference tree not mounted (GPU box)")
+def test_named_materials_against_the_reference_icons(oracle_lib):
+    """The only renderer output the reference ships: data/materials/<name>.png, OCCT path-traced renders of
+    preview.tcl.  Their environment map is not shipped, so absolute values and mirror-like metals cannot be
+    compared; what can is the ball's colour RELATIVE to the plaster ball of the same series (linear ratios).
+    Statistics of the icons: tests/golden/material_icons.json (made by make_material_icons.py)."""
+    import json
+    from cadrays_b200.view import V3d_View
+    from oracle.oracle_ffi import OracleScene
+    icons = json.loads((Path(__file__).parent / "golden" / "material_icons.json").read_text())
+    s = _preview_session(64)
+    yy, xx = np.mgrid[0:64, 0:64]
+    mask = ((xx - 31.5) ** 2 + (yy - 64 * 0.45) ** 2) < (64 * 0.18) ** 2
+    wanted = ("plaster", "plastic", "stone", "shiny_plastic", "satin", "neon_gnc", "jade", "charcoal", "obsidian",
+              "glass", "water", "neon_phc", "brass", "gold", "copper")
+    ours, ref = {}, {}
+    for path, _, d in s.dumps:
+        name = os.path.splitext(os.path.basename(path))[0]
+        if name not in wanted:
+            continue
+        v = V3d_View(host_only=True)
+        d.apply(v, with_target=False)
+        o = OracleScene(v.ExportBVH())
+        o.configure(d)
+        img = o.display(o.render(64, 64, 48))[::-1].astype(np.float64) / 255.0
+        o.close(); v.Remove()
+        ours[name] = img[mask].mean(0) ** 2                                   # display (gamma 2) -> linear
+        ref[name] = np.array(icons[ICON_OF.get(name, name)]["ball"]) ** 2
+    rel = lambda t, n: t[n] / t["plaster"]
+    for n in ("plastic", "stone", "shiny_plastic", "satin", "neon_gnc", "jade", "charcoal"):
+        assert np.allclose(rel(ours, n), rel(ref, n), rtol=0.25), (n, rel(ours, n), rel(ref, n))
+    assert np.allclose(rel(ours, "obsidian"), rel(ref, "obsidian"), atol=0.04)
+    for n, tol in (("glass", 0.10), ("water", 0.15)):                          # tint of the transmitted light
+        a, b = rel(ours, n), rel(ref, n)
+        assert abs(a[1] / a[0] - b[1] / b[0]) < tol * b[1] / b[0] and abs(a[2] / a[0] - b[2] / b[0]) < tol * b[2] / b[0], (n, a, b)
+    g = rel(ours, "neon_phc")
+    assert g[1] > 2.0 and g[1] > 1.5 * g[2] > 3.0 * g[0]                       # green glow, as neon.png
+    for n in ("brass", "gold", "copper"):                                      # hue only: warm metals
+        a, b = ours[n], ref[n]
+        assert a[0] > a[1] > a[2] and b[0] > b[1] > b[2]
+        assert abs(a[1] / a[0] - b[1] / b[0]) < 0.2, (n, a, b)
