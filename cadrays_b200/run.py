@@ -4,6 +4,10 @@ per pixel per Redraw(), like the reference's GUI loop), writes Output_<script>_<
 and Output_<script>_<N>.txt (average frames per second) -- the two files testing/CADRays_Testing.py reads.
 
   python -m cadrays_b200.run script.tcl N [--size WxH] [--out DIR] [--hdr] [--device 0] [--spp-per-redraw K]
+
+A script that renders by itself (`vfps N` followed by `vdump file`, as data/other/preview.tcl does for every named
+material) gets each dump rendered when the command is reached: N frames (capped by --max-dump-frames), written as
+<out>/<basename of file>.
 """
 from __future__ import annotations
 
@@ -24,11 +28,24 @@ def main(argv=None) -> int:
     ap.add_argument("--hdr", action="store_true")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--spp-per-redraw", type=int, default=1)
+    ap.add_argument("--max-dump-frames", type=int, default=8000)
     args = ap.parse_args(argv)
     w, h = (int(v) for v in args.size.lower().split("x"))
-    sess = tcl.load_script(args.script, w, h)
-    desc = sess.scene()
     view = V3d_View(args.device)
+    sess = tcl.DrawSession(w, h, root=os.path.dirname(os.path.abspath(args.script)))
+    sess.size_fixed = True
+
+    def on_dump(session, path, frames):
+        d = session.scene()
+        d.apply(view)
+        view.Redraw(max(1, min(frames or 1, args.max_dump_frames)))
+        target = os.path.join(args.out, os.path.basename(path.replace("\\", "/")))
+        imageio.write_png(os.path.splitext(target)[0] + ".png", view.BufferDump(Graphic3d_BT_RGB))
+
+    sess.on_dump = on_dump
+    with open(args.script, "r", encoding="utf-8", errors="replace") as f:
+        sess.eval(f.read())
+    desc = sess.scene()
     desc.apply(view)
     t0 = time.perf_counter()
     frames = 0

@@ -6,6 +6,8 @@ Three levels of BASELINE.json's north_star, all measured against OUR CPU restate
   level 2  single-sample radiance with the RNG reproduced       -> bit-exact (bound stated: 1e-4)
   level 3  converged images                                     -> bit-exact at equal spp
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -326,6 +328,38 @@ def test_tcl_script_headless_run_matches_oracle(tmp_path, product_lib, oracle_li
     orc.configure(desc)
     assert np.array_equal(png, orc.display(orc.render(96, 64, 6))[::-1])
     view.Remove()
+
+
+def test_headless_run_renders_every_vdump(tmp_path, product_lib, oracle_lib):
+    """A script that renders by itself -- `vfps N` + `vdump file` per material, the way data/other/preview.tcl makes
+    the material icons -- gets one PNG per vdump, each equal to the oracle's image of the scene at that point."""
+    from cadrays_b200 import imageio, run, tcl
+    from oracle.oracle_ffi import OracleScene
+    from tests.test_tcl_cpu import SCRIPT
+    loop = SCRIPT + """
+foreach aMat {gold jade glass} {
+  vsetmaterial m "$aMat"
+  vfps 5
+  vdump "D:/somewhere/else/$aMat.png"
+}
+"""
+    script = tmp_path / "Icons.tcl"
+    script.write_text(loop)
+    assert run.main([str(script), "2", "--size", "64x48", "--out", str(tmp_path)]) == 0
+    sess = tcl.DrawSession(64, 48, root=str(tmp_path))
+    sess.size_fixed = True
+    sess.eval(loop)
+    assert [os.path.basename(p) for p, _, _ in sess.dumps] == ["gold.png", "jade.png", "glass.png"]
+    view = V3d_View(host_only=True)
+    for path, frames, desc in sess.dumps:
+        desc.apply(view, with_target=False)
+        orc = OracleScene(view.ExportBVH())
+        orc.configure(desc)
+        png = imageio.read_png_rgb8(str(tmp_path / os.path.basename(path)))
+        assert frames == 5 and np.array_equal(png, orc.display(orc.render(64, 48, 5))[::-1]), path
+        orc.close()
+    view.Remove()
+    assert (tmp_path / "Output_Icons_2.png").exists()
 
 
 def test_level3_converged_4096spp(product_lib, oracle_lib):
