@@ -132,6 +132,7 @@ struct crt_context {
   bool l2_persist = false;      // L2 access-policy window over the scene arena (CRT_L2_PERSIST=1)
   // software pipeline: a wave is split into two half-waves on two streams so that the latency-bound shading of
   // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
+  bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
   bool pipeline = false;
   int pipeline_trace_ctas = 5;
   cudaStream_t stream2 = nullptr;
@@ -415,7 +416,10 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
   static const int r_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
   const int cap = trace_ctas > 0 ? c->sm_count * trace_ctas : (1 << 30);
   const int g_ext = std::min(r_ext, cap), g_con = std::min(r_con, cap), g_dual = std::min(r_dual, cap);
-  {
+  // camera rays computed inside the depth-0 kernels instead of a generate pass
+  const bool primary = c->fuse_primary && pers && !adaptive && (c->width & 7u) == 0 && (c->height & 3u) == 0;
+  static const int r_pri = resident_grid(c, k_extend_primary<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  if (!primary) {
     SpanGuard g(c, F_GENERATE, s);
     if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, *adaptive, d_seeds, n_batch);
     else k_generate<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, d_seeds, n_batch);
@@ -424,14 +428,20 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND, s);
-      if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
+      else if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE, s);
-      if (c->ds.n_tex) k_shade<COUNT, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc);
-      else k_shade<COUNT, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc);
+      if (primary && depth == 0) {
+        if (c->ds.n_tex) k_shade<COUNT, true, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        else k_shade<COUNT, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+      } else {
+        if (c->ds.n_tex) k_shade<COUNT, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        else k_shade<COUNT, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+      }
     }
     if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT, s);
@@ -625,6 +635,7 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_FUSE_PRIMARY")) c->fuse_primary = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(1, std::atoi(tv));
 

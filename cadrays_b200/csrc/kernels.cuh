@@ -907,11 +907,12 @@ __device__ __forceinline__ void flush_counters(Counters* g, const Counters& c)
 
 // ------------------------------------------------------------------ kernels
 
-// GenerateRay: camera ray of one sample of pixel (px, py) into path slot `slot`.
-__device__ __forceinline__ void generate_path(const PathState& st, const DeviceParams& P, uint32_t slot, uint32_t px, uint32_t py,
-                                          uint32_t frame_seed)
+// GenerateRay: camera ray of one sample of pixel (px, py); rng is the generator state after the
+// pixel jitter (and lens) draws.
+__device__ __forceinline__ void camera_ray(const DeviceParams& P, uint32_t px, uint32_t py, uint32_t frame_seed,
+                                           v3& o, v3& d, uint32_t& rng)
 {
-  uint32_t rng = seed_rand(frame_seed, px, py, P.width, P.rng_radius);
+  rng = seed_rand(frame_seed, px, py, P.width, P.rng_radius);
   const float jx = rand_float(rng);
   const float jy = rand_float(rng);
   float la = 0.0f, lb = 0.0f;
@@ -922,7 +923,6 @@ __device__ __forceinline__ void generate_path(const PathState& st, const DeviceP
   const float sy = fmaf(fy, 2.0f, -1.0f) * P.hh;
   const v3 eye = V(P.eye[0], P.eye[1], P.eye[2]);
   const v3 cu = V(P.cu[0], P.cu[1], P.cu[2]), cv = V(P.cv[0], P.cv[1], P.cv[2]), cw = V(P.cw[0], P.cw[1], P.cw[2]);
-  v3 o, d;
   if (P.is_ortho) {
     o = vadd(eye, vadd(vscale(cu, sx), vscale(cv, sy)));
     d = cw;
@@ -939,6 +939,15 @@ __device__ __forceinline__ void generate_path(const PathState& st, const DeviceP
     o = vadd(o, vadd(vscale(cu, r * cs), vscale(cv, r * sn)));
     d = normalize3(vsub(focus, o));
   }
+}
+
+// the camera ray of one sample of pixel (px, py) written into path slot `slot`
+__device__ __forceinline__ void generate_path(const PathState& st, const DeviceParams& P, uint32_t slot, uint32_t px, uint32_t py,
+                                              uint32_t frame_seed)
+{
+  v3 o, d;
+  uint32_t rng;
+  camera_ray(P, px, py, frame_seed, o, d, rng);
   st_stream(&st.ray_o[slot], make_float4(o.x, o.y, o.z, 1.0f));
   st_stream(&st.ray_d[slot], make_float4(d.x, d.y, d.z, __int_as_float(0)));
   st_stream(&st.thr[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng)));
@@ -1017,6 +1026,44 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
   if (COUNT) flush_counters(gcnt, cnt);
 }
 
+// Depth 0 without a generate pass: the camera ray of slot i is a pure function of (pixel, frame seed), so the
+// traversal kernel computes it when a lane takes slot i, and k_shade<.., FIRST> computes it again instead of
+// reading four float4 of path state that would only hold (ray, 1, 0).  Saves the k_generate launch and about
+// 160 bytes of HBM traffic per path.  Requires a tile-aligned resolution (every slot is a pixel).
+struct PrimaryPolicy {
+  PathState st;
+  const DeviceParams& P;
+  const uint32_t* __restrict__ seeds;
+  uint32_t per_sample;
+  __device__ __forceinline__ uint32_t load(uint32_t slot, v3& o, v3& d, float& tmax, bool&) const
+  {
+    const uint32_t k = slot / per_sample, in = slot - k * per_sample;
+    const uint32_t tile = in >> 5, lane = in & 31u;
+    uint32_t rng;
+    camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
+    tmax = CRT_MAXFLOAT;
+    return slot;
+  }
+  __device__ __forceinline__ void store(uint32_t slot, const Hit& hit, bool, bool) const
+  {
+    st_stream(&st.hit[slot], make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri)));
+    st_stream(&st.hit_inst[slot], (int32_t)hit.inst);
+  }
+};
+
+template <bool COUNT, bool QUAD>
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
+k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __restrict__ seeds, uint32_t n_batch, Counters* gcnt)
+{
+  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t n = per_sample * n_batch;
+  Counters cnt = {};
+  PrimaryPolicy pol{ st, P, seeds, per_sample };
+  trace_persistent<0, COUNT, QUAD>(S, n, st.work_extend, cnt, pol);
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = n;
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
 // One bounce of PathTrace for every active path: implicit
 // light / environment hit with MIS, emission, next-event estimation (emits a
 // shadow ray), Beer-Lambert absorption, layered-BSDF sampling, termination /
@@ -1024,9 +1071,9 @@ k_extend(DeviceScene S, PathState st, int depth, Counters* gcnt)
 #ifndef CRT_SHADE_MIN_BLOCKS
 #define CRT_SHADE_MIN_BLOCKS 8
 #endif
-template <bool COUNT, bool TEX>
+template <bool COUNT, bool TEX, bool FIRST>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
-k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
+k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds)
 {
   const uint32_t n = st.n_active[depth];
   const uint32_t* __restrict__ q = st.queue[depth & 1];
@@ -1047,14 +1094,28 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
     uint32_t rng = 0;
     bool inside = false;
     if (valid) {
-      slot = ld_stream(&q[i]);
-      const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]), hh = ld_stream(&st.hit[slot]);
-      float4 rr = ld_stream(&st.rad[slot]);
-      org = V(ro.x, ro.y, ro.z); dir = V(rd.x, rd.y, rd.z);
-      imp_pdf = ro.w;
-      inside = (__float_as_int(rd.w) & 1) != 0;
-      thr = V(tw.x, tw.y, tw.z);
-      rng = __float_as_uint(tw.w);
+      float4 hh, rr;
+      if (FIRST) {
+        // depth 0 after k_extend_primary: slot i is pixel sample i; its state is (camera ray, throughput 1, radiance 0)
+        slot = i;
+        const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+        const uint32_t k = slot / per_sample, in = slot - k * per_sample;
+        const uint32_t tile = in >> 5, ln = in & 31u;
+        camera_ray(P, (tile % P.tiles_x) * 8u + (ln & 7u), (tile / P.tiles_x) * 4u + (ln >> 3), __ldg(seeds + k), org, dir, rng);
+        thr = V(1.0f, 1.0f, 1.0f);
+        rr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        hh = ld_stream(&st.hit[slot]);
+      } else {
+        slot = ld_stream(&q[i]);
+        const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]);
+        hh = ld_stream(&st.hit[slot]);
+        rr = ld_stream(&st.rad[slot]);
+        org = V(ro.x, ro.y, ro.z); dir = V(rd.x, rd.y, rd.z);
+        imp_pdf = ro.w;
+        inside = (__float_as_int(rd.w) & 1) != 0;
+        thr = V(tw.x, tw.y, tw.z);
+        rng = __float_as_uint(tw.w);
+      }
       const int32_t tri = __float_as_int(hh.w);
       const bool found = tri >= 0;
       v3 radiance = V(rr.x, rr.y, rr.z);
@@ -1177,7 +1238,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt)
           want_next = true;
         }
       }
-      if (radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {
+      if (FIRST || radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {   // FIRST: this write initialises the slot
         rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
         st_stream(&st.rad[slot], rr);
       }
