@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--workload", default="assembly", choices=["assembly", "cornell", "materials", "instanced", "instanced_flat"])
     ap.add_argument("--bvh-width", type=int, default=2, choices=[2, 4], help="2 = binary BVH (default), 4 = OCCT's optional QUAD_BVH collapse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="1920x1080x8", help="WxHxSPP sample of the workload for the CPU legs")
+    ap.add_argument("--cpu-sample", default="1920x1080x32",
+                    help="WxHxSPP sample of the workload for the CPU legs (default: about 5 s per step on 16 cores)")
     return ap.parse_args()
 
 
