@@ -338,6 +338,10 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t pool_next = 0, pool_end = 0;   // warp-uniform
   bool drained = false;                   // warp-uniform: the launch's queue is exhausted
+  // rays a warp takes per atomic: kChunk while there is plenty of work; one ray per lane when the launch has fewer
+  // rays than that for every warp (late bounces, small frames), so that the work spreads over all warps instead of
+  // a few warps walking two rounds of long rays while the rest of the GPU idles
+  const uint32_t chunk = (n >= gridDim.x * (blockDim.x >> 5) * kChunk) ? kChunk : 32u;
   int32_t cur = kDone;
   bool has_ray = false, found = false, any_ray = (MODE == 1);
   uint32_t token = 0;
@@ -391,10 +395,10 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
     if (m) {
       if (pool_next == pool_end && !drained) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, kChunk);
+        if (lane == 0) base = atomicAdd(work, chunk);
         base = __shfl_sync(FULL, base, 0);
         if (base >= n) drained = true;
-        else { pool_next = base; pool_end = min(base + kChunk, n); }
+        else { pool_next = base; pool_end = min(base + chunk, n); }
       }
       const uint32_t avail = pool_end - pool_next;
       const uint32_t rank = __popc(m & ((1u << lane) - 1u));
