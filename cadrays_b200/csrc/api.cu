@@ -132,6 +132,7 @@ struct crt_context {
   bool l2_persist = false;      // L2 access-policy window over the scene arena (CRT_L2_PERSIST=1)
   // software pipeline: a wave is split into two half-waves on two streams so that the latency-bound shading of
   // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
+  bool shade_sort = true;       // hit / miss grouping inside k_shade after the first bounce (CRT_SHADE_SORT=0 disables)
   bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
   bool pipeline = false;
   int pipeline_trace_ctas = 5;
@@ -436,11 +437,14 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
     {
       SpanGuard g(c, F_SHADE, s);
       if (primary && depth == 0) {
-        if (c->ds.n_tex) k_shade<COUNT, true, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
-        else k_shade<COUNT, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        if (c->ds.n_tex) k_shade<COUNT, true, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        else k_shade<COUNT, false, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+      } else if (c->shade_sort && depth > 0) {
+        if (c->ds.n_tex) k_shade<COUNT, true, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        else k_shade<COUNT, false, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
       } else {
-        if (c->ds.n_tex) k_shade<COUNT, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
-        else k_shade<COUNT, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        if (c->ds.n_tex) k_shade<COUNT, true, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        else k_shade<COUNT, false, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
       }
     }
     if (!fuse || depth == depth_max - 1) {
@@ -635,6 +639,7 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_SHADE_SORT")) c->shade_sort = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_FUSE_PRIMARY")) c->fuse_primary = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(1, std::atoi(tv));

@@ -1078,7 +1078,14 @@ k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __
 #ifndef CRT_SHADE_MIN_BLOCKS
 #define CRT_SHADE_MIN_BLOCKS 8
 #endif
-template <bool COUNT, bool TEX, bool FIRST>
+// SORT (bounces after the first): a CTA takes kShadeBatch queue entries at a time, files them in shared memory
+// under "hit a surface" (from the front) and "missed" (from the back), then shades the two groups one after the
+// other, so that the lanes of a warp run the same branch of the bounce.  Only the order changes.
+#ifndef CRT_SHADE_BATCH
+#define CRT_SHADE_BATCH 512
+#endif
+constexpr uint32_t kShadeBatch = CRT_SHADE_BATCH;
+template <bool COUNT, bool TEX, bool FIRST, bool SORT>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds)
 {
@@ -1086,14 +1093,49 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
   const uint32_t* __restrict__ q = st.queue[depth & 1];
   uint32_t* __restrict__ qn = st.queue[(depth + 1) & 1];
   Counters cnt = {};
-  const uint32_t stride = gridDim.x * blockDim.x;
   const bool two_sided = P.two_sided != 0;
   const float eps = S.scene_eps;
-  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-    const uint32_t i = base + (threadIdx.x & 31u);
-    const bool valid = i < n;
-    bool want_shadow = false, want_next = false;
+  __shared__ uint32_t s_list[SORT ? kShadeBatch : 1];
+  __shared__ uint32_t s_cnt[2];
+  const uint32_t batch = SORT ? kShadeBatch : 128u;
+  for (uint32_t bbase = blockIdx.x * batch; bbase < n; bbase += gridDim.x * batch) {
+   uint32_t n_iter = 1, n_hit = 0, n_hit_pad = 0, n_miss = 0;
+   if (SORT) {
+     __syncthreads();                       // the previous batch's list is no longer read
+     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+     __syncthreads();
+     const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll 1
+     for (uint32_t k = 0; k < kShadeBatch / 128u; ++k) {
+       const uint32_t e = bbase + k * 128u + threadIdx.x;
+       const bool ok = e < n;
+       uint32_t sl = 0;
+       bool found = false;
+       if (ok) { sl = ld_stream(&q[e]); found = __float_as_int(ld_stream(&st.hit[sl]).w) >= 0; }
+       const unsigned mh = __ballot_sync(0xffffffffu, ok && found), mm = __ballot_sync(0xffffffffu, ok && !found);
+       uint32_t bh = 0, bm = 0;
+       if (lane == 0) { if (mh) bh = atomicAdd(&s_cnt[0], (uint32_t)__popc(mh)); if (mm) bm = atomicAdd(&s_cnt[1], (uint32_t)__popc(mm)); }
+       bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+       const unsigned below = (1u << lane) - 1u;
+       if (ok && found) s_list[bh + __popc(mh & below)] = sl;
+       if (ok && !found) s_list[kShadeBatch - 1u - (bm + __popc(mm & below))] = sl;
+     }
+     __syncthreads();
+     n_hit = s_cnt[0]; n_miss = s_cnt[1];
+     n_hit_pad = (n_hit + 31u) & ~31u;      // the misses start on a warp boundary
+     n_iter = (n_hit_pad + n_miss + 127u) / 128u;
+   }
+#pragma unroll 1
+   for (uint32_t it = 0; it < n_iter; ++it) {
+    uint32_t i = bbase + threadIdx.x;
+    bool valid = i < n;
     uint32_t slot = 0;
+    if (SORT) {
+      const uint32_t e = it * 128u + threadIdx.x;
+      valid = e < n_hit || (e >= n_hit_pad && e < n_hit_pad + n_miss);
+      if (valid) slot = e < n_hit ? s_list[e] : s_list[kShadeBatch - 1u - (e - n_hit_pad)];
+    }
+    bool want_shadow = false, want_next = false;
     v3 sh_o = V(0, 0, 0), sh_d = V(0, 0, 0), sh_c = V(0, 0, 0);
     float sh_tmax = 0.0f;
     v3 org = V(0, 0, 0), dir = V(0, 0, 1), thr = V(0, 0, 0);
@@ -1113,7 +1155,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
         rr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         hh = ld_stream(&st.hit[slot]);
       } else {
-        slot = ld_stream(&q[i]);
+        if (!SORT) slot = ld_stream(&q[i]);
         const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]);
         hh = ld_stream(&st.hit[slot]);
         rr = ld_stream(&st.rad[slot]);
@@ -1264,6 +1306,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
       st_stream(&st.ray_d[slot], make_float4(dir.x, dir.y, dir.z, __int_as_float(inside ? 1 : 0)));
       st_stream(&st.thr[slot], make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng)));
     }
+   }
   }
   if (COUNT) flush_counters(gcnt, cnt);
 }
