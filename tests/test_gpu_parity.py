@@ -570,3 +570,26 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
     assert checked > 100_000
     view.BindAccum(None)
     view.Remove()
+
+
+# ------------------------------------------------------------------ every A/B knob keeps the result
+
+@pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static", "CRT_PIPELINE=1"])
+def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracle_lib):
+    """The environment knobs read by crt_create select alternative kernels / launch structures (unsorted shading,
+    a separate generate pass, unfused shadow + extend launches, the static traversal loop, the two-stream half-wave
+    pipeline).  They are performance A/B switches: images, work counters and any-hit answers must not change."""
+    name, value = knob.split("=")
+    monkeypatch.setenv(name, value)
+    desc = scenes.materials_scene(160, 96, depth=8, sphere_res=(32, 16))
+    desc.params.SamplesPerBatch = 4
+    view, orc = _pair(desc)              # the context is created with the knob in the environment
+    view.EnableStats(True); view.ResetStats()
+    view.Redraw(8)                        # two waves of 4 (two half-waves each when pipelined)
+    st = view.Stats()
+    view.EnableStats(False)
+    acc, ost = orc.render(desc.width, desc.height, 8, stats=True)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), orc.hdr(acc)), knob
+    for k in ("rays_nearest", "rays_any", "n_inner", "n_tri", "n_inner_any", "n_tri_any", "shaded_hits", "samples"):
+        assert st[k] == ost[k], (knob, k)
+    view.Remove()
