@@ -133,6 +133,9 @@ struct crt_context {
   // software pipeline: a wave is split into two half-waves on two streams so that the latency-bound shading of
   // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
   bool shade_sort = true;       // hit / miss grouping inside k_shade after the first bounce (CRT_SHADE_SORT=0 disables)
+  bool primary_lockstep = true; // camera rays walked in lockstep per 8x4 tile instead of per-lane refill (CRT_PRIMARY_LOCKSTEP=0)
+  int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
+                                // 18.90 / 18.80 / 18.57 / 18.45 / 18.43 / 18.47 ms of traversal per step)
   bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
   bool pipeline = false;
   int pipeline_trace_ctas = 5;
@@ -429,7 +432,9 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND, s);
-      if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
+      if (primary && depth == 0 && !QUAD && c->primary_lockstep)
+        k_extend_primary_lockstep<COUNT><<<grid_for(c, c->primary_grid), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
+      else if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
       else if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
@@ -640,6 +645,8 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_SHADE_SORT")) c->shade_sort = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_PRIMARY_LOCKSTEP")) c->primary_lockstep = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_PRIMARY_GRID")) c->primary_grid = std::max(1, std::atoi(tv));
   if (const char* tv = std::getenv("CRT_FUSE_PRIMARY")) c->fuse_primary = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(1, std::atoi(tv));

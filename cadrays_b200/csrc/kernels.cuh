@@ -1071,6 +1071,32 @@ k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __
   if (COUNT) flush_counters(gcnt, cnt);
 }
 
+// The same for the binary tree in lockstep: a warp takes the 32 slots of one 8x4 pixel tile and walks them together
+// (no per-lane refill).  Camera rays of a tile visit nearly the same nodes, so staying in step keeps most lanes active
+// (the persistent driver mixes rays at different stages in a warp: 14.8 of 32 lanes, issue slots 78 % busy).
+template <bool COUNT>
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
+k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __restrict__ seeds, uint32_t n_batch, Counters* gcnt)
+{
+  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t n = per_sample * n_batch;
+  Counters cnt = {};
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+    const uint32_t k = slot / per_sample, in = slot - k * per_sample;
+    const uint32_t tile = in >> 5, lane = in & 31u;
+    v3 o, d;
+    uint32_t rng;
+    camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
+    Hit hit;
+    traverse<false, COUNT>(S, o, d, CRT_MAXFLOAT, hit, cnt);
+    if (COUNT) cnt.rays_nearest++;
+    st_stream(&st.hit[slot], make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri)));
+    st_stream(&st.hit_inst[slot], (int32_t)hit.inst);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = n;
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
 // One bounce of PathTrace for every active path: implicit
 // light / environment hit with MIS, emission, next-event estimation (emits a
 // shadow ray), Beer-Lambert absorption, layered-BSDF sampling, termination /

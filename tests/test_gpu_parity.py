@@ -574,7 +574,8 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
 
 # ------------------------------------------------------------------ every A/B knob keeps the result
 
-@pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static", "CRT_PIPELINE=1"])
+@pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_PRIMARY_LOCKSTEP=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static",
+                                  "CRT_PIPELINE=1"])
 def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracle_lib):
     """The environment knobs read by crt_create select alternative kernels / launch structures (unsorted shading,
     a separate generate pass, unfused shadow + extend launches, the static traversal loop, the two-stream half-wave
