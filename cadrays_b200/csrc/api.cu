@@ -436,8 +436,9 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
         k_extend_primary_lockstep<COUNT><<<grid_for(c, c->primary_grid), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
       else if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
       else if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
-      else if (pers) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
-      else k_extend<COUNT, false, false><<<grid_for(c, 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      else if (pers && !(depth == 0 && !QUAD && c->primary_lockstep)) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
+      // camera rays that went through a generate pass (adaptive sampling, ragged sizes): lockstep as well
+      else k_extend<COUNT, false, false><<<grid_for(c, depth == 0 ? c->primary_grid : 16), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
     }
     {
       SpanGuard g(c, F_SHADE, s);
