@@ -132,6 +132,8 @@ struct crt_context {
   bool l2_persist = false;      // L2 access-policy window over the scene arena (CRT_L2_PERSIST=1)
   // software pipeline: a wave is split into two half-waves on two streams so that the latency-bound shading of
   // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
+  bool mats_lean = false;       // no material has a coat or transmission: k_shade<.., LEAN> (CRT_SHADE_LEAN=0 disables)
+  bool shade_lean = true;
   bool shade_sort = true;       // hit / miss grouping inside k_shade after the first bounce (CRT_SHADE_SORT=0 disables)
   bool primary_lockstep = true; // camera rays walked in lockstep per 8x4 tile instead of per-lane refill (CRT_PRIMARY_LOCKSTEP=0)
   int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
@@ -347,6 +349,10 @@ int upload_tables(crt_context* c)
     if (!c->mats.empty())
       CRT_CUDA(cudaMemcpyAsync(c->d_mats.p, c->mats.data(), c->mats.size() * sizeof(crt_bsdf), cudaMemcpyHostToDevice, c->stream));
     c->ds.mats = c->d_mats.p; c->ds.n_mats = (uint32_t)c->mats.size();
+    c->mats_lean = c->shade_lean;
+    for (const crt_bsdf& m : c->mats)
+      for (int k = 0; k < 3; ++k)
+        if (m.Kc[k] != 0.0f || m.Kt[k] != 0.0f) c->mats_lean = false;
     c->mats_dirty = false;
   }
   if (c->lights_dirty) {
@@ -442,16 +448,17 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
     }
     {
       SpanGuard g(c, F_SHADE, s);
+      const dim3 sg(grid_for(c, 8));
+#define CRT_SHADE(TEXV, FIRSTV, SORTV, LEANV) k_shade<COUNT, TEXV, FIRSTV, SORTV, LEANV><<<sg, 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds)
+      const bool lean = c->mats_lean && !c->ds.n_tex;
       if (primary && depth == 0) {
-        if (c->ds.n_tex) k_shade<COUNT, true, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
-        else k_shade<COUNT, false, true, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        if (c->ds.n_tex) CRT_SHADE(true, true, false, false); else if (lean) CRT_SHADE(false, true, false, true); else CRT_SHADE(false, true, false, false);
       } else if (c->shade_sort && depth > 0) {
-        if (c->ds.n_tex) k_shade<COUNT, true, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
-        else k_shade<COUNT, false, false, true><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        if (c->ds.n_tex) CRT_SHADE(true, false, true, false); else if (lean) CRT_SHADE(false, false, true, true); else CRT_SHADE(false, false, true, false);
       } else {
-        if (c->ds.n_tex) k_shade<COUNT, true, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
-        else k_shade<COUNT, false, false, false><<<grid_for(c, 8), 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds);
+        if (c->ds.n_tex) CRT_SHADE(true, false, false, false); else if (lean) CRT_SHADE(false, false, false, true); else CRT_SHADE(false, false, false, false);
       }
+#undef CRT_SHADE
     }
     if (!fuse || depth == depth_max - 1) {
       SpanGuard g(c, F_CONNECT, s);
@@ -645,6 +652,7 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_TRAVERSAL")) c->persistent = std::string(tv) != "static";
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_SHADE_LEAN")) c->shade_lean = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_SHADE_SORT")) c->shade_sort = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_LOCKSTEP")) c->primary_lockstep = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_GRID")) c->primary_grid = std::max(1, std::atoi(tv));

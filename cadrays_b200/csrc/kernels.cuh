@@ -703,6 +703,10 @@ __device__ __forceinline__ v3 transmitted(float index, v3 wo)
   return normalize3(V(-eta * wo.x, -eta * wo.y, cos_t));
 }
 
+// LEAN: the scene's material table has no coat and no transmission (Kc = Kt = 0 for every material), so those
+// lobes can never be chosen; the instantiation drops their code.  pc and pt are still computed (they are +0) so
+// that every remaining value is the same bit pattern as in the full version.
+template <bool LEAN>
 __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& wi, v3& weight, bool& inside,
                                                      uint32_t& rng, bool two_sided)
 {
@@ -716,7 +720,7 @@ __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& w
   float total = (pc + pd) + (ps + pt);
   float ksi = total * rand_float(rng);
   wi = V(0, 0, 1);
-  if (ksi < pc) {
+  if (!LEAN && ksi < pc) {
     pdf = pc / total;
     weight = vmul(weight, vscale(b.Kc, 1.0f / pdf));
     if (b.Kc_w < CRT_FLT_EPS) {
@@ -732,7 +736,7 @@ __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& w
       pdf = pd / total;
       weight = vmul(weight, vscale(b.Kd, 1.0f / pdf));
       weight = vmul(weight, sample_lambert(wo, wi, pdf, rng, two_sided));
-    } else if (ksi < (pc + pd) + ps) {
+    } else if (LEAN || ksi < (pc + pd) + ps) {
       pdf = ps / total;
       weight = vmul(weight, vscale(b.Ks, 1.0f / pdf));
       if (b.Ks_w < CRT_FLT_EPS) {
@@ -1111,7 +1115,7 @@ k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uin
 #define CRT_SHADE_BATCH 512
 #endif
 constexpr uint32_t kShadeBatch = CRT_SHADE_BATCH;
-template <bool COUNT, bool TEX, bool FIRST, bool SORT>
+template <bool COUNT, bool TEX, bool FIRST, bool SORT, bool LEAN>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds)
 {
@@ -1265,6 +1269,10 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
         }
 
         const v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), frame);
+        if (LEAN) {   // host guarantee: no coat, no transmission anywhere in the material table (and so never inside a medium)
+          B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kt = V(0, 0, 0);
+          inside = false;
+        }
         radiance = vadd(radiance, vmul(thr, mat_le));
 
         const v3 nee_k = vadd(B.Kd, vadd(B.Ks_w > CRT_FLT_EPS ? B.Ks : V(0, 0, 0), B.Kc_w > CRT_FLT_EPS ? B.Kc : V(0, 0, 0)));
@@ -1299,7 +1307,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
         }
 
         v3 wi;
-        imp_pdf = sample_bsdf_layered(B, wo, wi, thr, inside, rng, two_sided);
+        imp_pdf = sample_bsdf_layered<LEAN>(B, wo, wi, thr, inside, rng, two_sided);
 
         float survive = any_gt(thr, CRT_MIN_THROUGHPUT) ? 1.0f : 0.0f;
         const bool rr_on = P.russian_roulette && depth >= 3;

@@ -575,14 +575,15 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
 # ------------------------------------------------------------------ every A/B knob keeps the result
 
 @pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_PRIMARY_LOCKSTEP=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static",
-                                  "CRT_PIPELINE=1"])
+                                  "CRT_PIPELINE=1", "CRT_SHADE_LEAN=0"])
 def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracle_lib):
     """The environment knobs read by crt_create select alternative kernels / launch structures (unsorted shading,
     a separate generate pass, unfused shadow + extend launches, the static traversal loop, the two-stream half-wave
     pipeline).  They are performance A/B switches: images, work counters and any-hit answers must not change."""
     name, value = knob.split("=")
     monkeypatch.setenv(name, value)
-    desc = scenes.materials_scene(160, 96, depth=8, sphere_res=(32, 16))
+    # the lean shading kernel only exists for scenes without coat / transmission: the assembly has neither
+    desc = _small_assembly() if name == "CRT_SHADE_LEAN" else scenes.materials_scene(160, 96, depth=8, sphere_res=(32, 16))
     desc.params.SamplesPerBatch = 4
     view, orc = _pair(desc)              # the context is created with the knob in the environment
     view.EnableStats(True); view.ResetStats()
