@@ -237,12 +237,28 @@ def run_ours(args):
     torch.cuda.synchronize()
     view.BindAccum(accum.data_ptr(), accum.numel() * 4)
 
+    # the all-reduce of step s runs on its own stream while the context stream already traces step s + 1:
+    # snapshot the sums (device copy, context stream), hand the snapshot to the communication stream, and let the
+    # next snapshot wait until the previous all-reduce has consumed the buffer
+    comm = torch.cuda.Stream(device=torch.device("cuda", local)) if world > 1 else None
+    reduce_done = torch.cuda.Event() if world > 1 else None
+    snapshot_ready = torch.cuda.Event() if world > 1 else None
+
     def one_step(step_index):
         view.SetNextSample(D.step_sample_start(step_index, rank, world, B))
         view.RedrawAsync(B)
         if world > 1:
+            stream.wait_event(reduce_done)           # no-op before the first record
             reduced.copy_(accum, non_blocking=True)
-            dist.all_reduce(reduced)
+            snapshot_ready.record(stream)
+            comm.wait_event(snapshot_ready)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(reduced)
+                reduce_done.record(comm)
+
+    def join_comm():
+        if world > 1:
+            stream.wait_event(reduce_done)           # the timed region ends after the last all-reduce
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,6 +280,7 @@ def run_ours(args):
         ev0.record(stream)
         for s in range(args.steps):
             one_step(args.warmup + s)
+        join_comm()
         ev1.record(stream)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
