@@ -236,6 +236,21 @@ def test_cpp_host_mirror_compiles_and_runs(tmp_path, product_lib):
     assert "blob" in r.stdout
 
 
+def test_c_abi_header_is_plain_c(tmp_path, product_lib):
+    """include/cadrays_b200.h compiles as C99 (-pedantic -Werror) and a C host can assemble a scene, set the
+    parameters, build / export the BVH and gets a loud refusal from every device call without a GPU."""
+    import subprocess
+    exe = tmp_path / "c_abi_check"
+    lib = REPO / "cadrays_b200" / "libcadrays_b200.so"
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{REPO / 'include'}", str(REPO / "tests" / "cpp" / "c_abi_check.c"),
+           "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "c abi ok" in r.stdout
+
+
 def test_recommit_after_edit_equals_fresh_build(product_lib):
     """Scene edits (SetLocation / material index) reuse the cached bottom trees; the resulting blob is the one a
     fresh build of the edited scene gives, and undoing the edit restores the original bytes."""
