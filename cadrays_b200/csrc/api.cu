@@ -385,17 +385,21 @@ int upload_tables(crt_context* c)
 
 int grid_for(const crt_context* c, int blocks_per_sm) { return c->sm_count * blocks_per_sm; }
 
-// grid of a persistent kernel = the CTAs that are resident at once (SM count x occupancy)
+// resident CTAs per SM of a kernel (a property of the kernel and the architecture, so callers may cache it)
 template <typename K>
-int resident_grid(const crt_context* c, K kernel, int block)
+int resident_per_sm(K kernel, int block)
 {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 4;
   }
-  return c->sm_count * per_sm;
+  return per_sm;
 }
+
+// grid of a persistent kernel = the CTAs that are resident at once on this context's device
+template <typename K>
+int resident_grid(const crt_context* c, K kernel, int block) { return c->sm_count * resident_per_sm(kernel, block); }
 
 PathState make_state(crt_context* c, size_t slot0, int half)
 {
@@ -421,14 +425,16 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
   Counters* gc = c->d_counters.p;
   const bool pers = c->persistent || QUAD;      // the 4-wide walk exists in the persistent driver only
   const bool fuse = pers && c->fuse_traversal;
-  static const int r_ext = resident_grid(c, k_extend<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
-  static const int r_con = resident_grid(c, k_connect<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
-  static const int r_dual = resident_grid(c, k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  static const int p_ext = resident_per_sm(k_extend<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int p_con = resident_per_sm(k_connect<COUNT, true, QUAD>, CRT_TRACE_BLOCK);
+  static const int p_dual = resident_per_sm(k_trace_dual<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  const int r_ext = c->sm_count * p_ext, r_con = c->sm_count * p_con, r_dual = c->sm_count * p_dual;
   const int cap = trace_ctas > 0 ? c->sm_count * trace_ctas : (1 << 30);
   const int g_ext = std::min(r_ext, cap), g_con = std::min(r_con, cap), g_dual = std::min(r_dual, cap);
   // camera rays computed inside the depth-0 kernels instead of a generate pass
   const bool primary = c->fuse_primary && pers && !adaptive && (c->width & 7u) == 0 && (c->height & 3u) == 0;
-  static const int r_pri = resident_grid(c, k_extend_primary<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  static const int p_pri = resident_per_sm(k_extend_primary<COUNT, QUAD>, CRT_TRACE_BLOCK);
+  const int r_pri = c->sm_count * p_pri;
   if (!primary) {
     SpanGuard g(c, F_GENERATE, s);
     if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, *adaptive, d_seeds, n_batch);
