@@ -5,8 +5,15 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <thread>
+#include <cstdio>
 #include <unordered_map>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace crt {
 
@@ -43,15 +50,53 @@ struct Box {
 // cheapest of (nbins-1) planes per axis; primitives are binned by centroid.
 // A degenerate split falls back to an index median.  The two children of a node
 // are allocated next to each other.
-void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<TreeNode>& nodes, int& max_depth)
+//
+// build_range builds the subtree over prims[lo, hi) into `nodes` (nodes[0] = its root, child indices local to
+// `nodes`, leaf ranges in global primitive indices).  With stop_count > 0 a node of at most stop_count primitives
+// (other than the root) is not subdivided but recorded in `tasks` and marked a = -1 - task index: the upper part of
+// a large tree is built serially this way, the recorded subtrees in parallel, and stitch_tree() renumbers
+// everything into exactly the node order the serial algorithm produces (children allocated when the parent is
+// processed, depth first, left first) -- the blob does not depend on the number of threads.
+struct BuildTask { int lo, hi, depth; };
+
+// Runs fn(part, begin, end) on `parts` contiguous slices of [lo, hi), each on its own std::thread.  Used for the
+// passes over the few very large nodes at the top of a big tree; plain threads rather than OpenMP regions because
+// the regions are short and frequent, and spinning OpenMP workers between them slowed the serial code in between
+// several-fold on the hosts measured.
+template <class F>
+void parallel_slices(int lo, int hi, int parts, F fn)
+{
+  std::vector<std::thread> pool;
+  const long n = (long)hi - lo;
+  for (int p = 1; p < parts; ++p)
+    pool.emplace_back([=] { fn(p, lo + (int)(n * p / parts), lo + (int)(n * (p + 1) / parts)); });
+  fn(0, lo, lo + (int)(n / parts));
+  for (std::thread& t : pool) t.join();
+}
+
+inline int build_threads()
+{
+  static const int n = [] {
+    int v = (int)std::thread::hardware_concurrency();
+#ifdef _OPENMP
+    v = std::min(v, omp_get_max_threads());
+#endif
+    return std::max(1, std::min(v, 32));
+  }();
+  return n;
+}
+constexpr int kWideNodeMin = 65536;   // primitives; see build_range
+
+void build_range(std::vector<Prim>& prims, int lo, int hi, int depth0, int leaf_size, int nbins, std::vector<TreeNode>& nodes,
+                 int& max_depth, int stop_count, std::vector<BuildTask>* tasks)
 {
   nodes.clear();
-  max_depth = 0;
-  if (prims.empty()) return;
+  max_depth = depth0;
+  if (hi <= lo) return;
   struct Work { int node, lo, hi, depth; };
   std::vector<Work> stack;
   nodes.push_back(TreeNode{});
-  stack.push_back({ 0, 0, (int)prims.size(), 0 });
+  stack.push_back({ 0, lo, hi, depth0 });
   std::vector<int> bin_count(nbins);
   std::vector<Box> bin_box(nbins);
   std::vector<float> right_area(nbins);
@@ -61,12 +106,32 @@ void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<
     Work w = stack.back();
     stack.pop_back();
     max_depth = std::max(max_depth, w.depth);
+    // the few nodes at the top of a large tree hold most of the primitives: their two passes (bounds, binning) run
+    // on all threads with per-thread partial results; min / max / integer counts do not depend on the order
+    const bool wide = (w.hi - w.lo) >= kWideNodeMin;
     Box nb, cb;
-    for (int i = w.lo; i < w.hi; ++i) { nb.grow(prims[i].lo, prims[i].hi); cb.grow_pt(prims[i].c); }
+    if (wide) {
+      const int parts = build_threads();
+      std::vector<Box> pnb(parts), pcb(parts);
+      parallel_slices(w.lo, w.hi, parts, [&](int p, int a, int b) {
+        Box lnb, lcb;
+        for (int i = a; i < b; ++i) { lnb.grow(prims[i].lo, prims[i].hi); lcb.grow_pt(prims[i].c); }
+        pnb[p] = lnb; pcb[p] = lcb;
+      });
+      for (int p = 0; p < parts; ++p) { nb.grow(pnb[p].lo, pnb[p].hi); cb.grow(pcb[p].lo, pcb[p].hi); }
+    } else {
+      for (int i = w.lo; i < w.hi; ++i) { nb.grow(prims[i].lo, prims[i].hi); cb.grow_pt(prims[i].c); }
+    }
     TreeNode nd;
     std::memcpy(nd.lo, nb.lo, 12);
     std::memcpy(nd.hi, nb.hi, 12);
     const int count = w.hi - w.lo;
+    if (stop_count > 0 && w.node != 0 && count <= stop_count && count > leaf_size && w.depth < kMaxTreeDepth) {
+      nd.leaf = false; nd.a = -1 - (int32_t)tasks->size(); nd.b = 0;
+      nodes[w.node] = nd;
+      tasks->push_back({ w.lo, w.hi, w.depth });
+      continue;
+    }
     if (count <= leaf_size || w.depth >= kMaxTreeDepth) {
       nd.leaf = true; nd.a = w.lo; nd.b = w.hi - 1;
       nodes[w.node] = nd;
@@ -80,10 +145,28 @@ void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<
       const float scale = (float)nbins / ext;
       std::fill(bin_count.begin(), bin_count.end(), 0);
       std::fill(bin_box.begin(), bin_box.end(), Box{});
-      for (int i = w.lo; i < w.hi; ++i) {
-        int b = std::min(nbins - 1, (int)((prims[i].c[axis] - cmin) * scale));
-        bin_count[b]++;
-        bin_box[b].grow(prims[i].lo, prims[i].hi);
+      if (wide) {
+        const int parts = build_threads();
+        std::vector<std::vector<int>> pc(parts, std::vector<int>(nbins, 0));
+        std::vector<std::vector<Box>> pb(parts, std::vector<Box>(nbins));
+        parallel_slices(w.lo, w.hi, parts, [&](int p, int a, int e) {
+          std::vector<int> lc(nbins, 0);
+          std::vector<Box> lb(nbins);
+          for (int i = a; i < e; ++i) {
+            int b = std::min(nbins - 1, (int)((prims[i].c[axis] - cmin) * scale));
+            lc[b]++;
+            lb[b].grow(prims[i].lo, prims[i].hi);
+          }
+          pc[p] = lc; pb[p] = lb;
+        });
+        for (int p = 0; p < parts; ++p)
+          for (int b = 0; b < nbins; ++b) { bin_count[b] += pc[p][b]; if (pc[p][b]) bin_box[b].grow(pb[p][b].lo, pb[p][b].hi); }
+      } else {
+        for (int i = w.lo; i < w.hi; ++i) {
+          int b = std::min(nbins - 1, (int)((prims[i].c[axis] - cmin) * scale));
+          bin_count[b]++;
+          bin_box[b].grow(prims[i].lo, prims[i].hi);
+        }
       }
       Box acc;
       int cnt = 0;
@@ -125,6 +208,72 @@ void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<
     stack.push_back({ nd.b, mid, w.hi, w.depth + 1 });
     stack.push_back({ nd.a, w.lo, mid, w.depth + 1 });
   }
+}
+
+void stitch_tree(const std::vector<TreeNode>& upper, const std::vector<std::vector<TreeNode>>& sub, std::vector<TreeNode>& out)
+{
+  out.clear();
+  out.push_back(TreeNode{});
+  struct Item { int32_t upper_idx, final_idx; };
+  std::vector<Item> stack{ { 0, 0 } };
+  while (!stack.empty()) {
+    const Item it = stack.back();
+    stack.pop_back();
+    const TreeNode& un = upper[(size_t)it.upper_idx];
+    if (!un.leaf && un.a < 0) {
+      // a subtree built on its own: its root takes the id the parent reserved, its descendants follow as one block
+      const std::vector<TreeNode>& local = sub[(size_t)(-1 - un.a)];
+      const int32_t base = (int32_t)out.size();
+      auto remap = [base](TreeNode n) { if (!n.leaf) { n.a = base + (n.a - 1); n.b = base + (n.b - 1); } return n; };
+      out[(size_t)it.final_idx] = remap(local[0]);
+      for (size_t j = 1; j < local.size(); ++j) out.push_back(remap(local[j]));
+    } else if (un.leaf) {
+      out[(size_t)it.final_idx] = un;
+    } else {
+      TreeNode nd = un;
+      nd.a = (int32_t)out.size();
+      nd.b = nd.a + 1;
+      out[(size_t)it.final_idx] = nd;
+      out.push_back(TreeNode{});
+      out.push_back(TreeNode{});
+      stack.push_back({ un.b, nd.b });
+      stack.push_back({ un.a, nd.a });
+    }
+  }
+}
+
+constexpr int kParallelBuildMin = 200000;   // primitives; smaller trees are built by one thread (meshes run in parallel anyway)
+
+void build_tree(std::vector<Prim>& prims, int leaf_size, int nbins, std::vector<TreeNode>& nodes, int& max_depth)
+{
+  const int n = (int)prims.size();
+  const bool force_serial = std::getenv("CRT_BUILD_SERIAL") != nullptr;   // A/B and the determinism test
+  if (n < kParallelBuildMin || force_serial) {
+    build_range(prims, 0, n, 0, leaf_size, nbins, nodes, max_depth, 0, nullptr);
+    return;
+  }
+  const bool timing = std::getenv("CRT_BUILD_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[build_tree] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+    t0 = now;
+  };
+  std::vector<TreeNode> upper;
+  std::vector<BuildTask> tasks;
+  build_range(prims, 0, n, 0, leaf_size, nbins, upper, max_depth, std::max(16384, n / 128), &tasks);
+  lap("upper levels");
+  std::vector<std::vector<TreeNode>> sub(tasks.size());
+  std::vector<int> sub_depth(tasks.size(), 0);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long t = 0; t < (long)tasks.size(); ++t)
+    build_range(prims, tasks[(size_t)t].lo, tasks[(size_t)t].hi, tasks[(size_t)t].depth, leaf_size, nbins, sub[(size_t)t],
+                sub_depth[(size_t)t], 0, nullptr);
+  for (int d : sub_depth) max_depth = std::max(max_depth, d);
+  lap("subtrees");
+  stitch_tree(upper, sub, nodes);
+  lap("stitch");
 }
 
 // BVH_QuadTree collapse (SURVEY A.3 "optional QUAD_BVH"; north_star: "per-mesh quad trees"): every inner
@@ -191,6 +340,15 @@ using MeshTree = BottomTree;
 
 bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string& err, int bvh_width)
 {
+  const bool timing = std::getenv("CRT_BUILD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[build_blob] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+
   const bool quad = bvh_width == 4;
   const size_t n_mesh = scene.meshes.size();
   const size_t n_inst = scene.instances.size();
@@ -202,17 +360,17 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     used[in.mesh] = 1;
   }
 
-  // bottom-level trees, one per referenced mesh
-#pragma omp parallel for schedule(dynamic, 1)
-  for (long mi = 0; mi < (long)n_mesh; ++mi) {
-    if (!used[mi] || trees[mi].built) continue;
+  // bottom-level trees, one per referenced mesh: large meshes one after the other (build_tree spreads each over the
+  // threads), then the small ones in parallel
+  auto build_mesh_tree = [&](size_t mi) {
     const Mesh& m = scene.meshes[mi];
     const size_t nt = m.idx.size() / 3;
     std::vector<Prim> prims(nt);
-    for (size_t t = 0; t < nt; ++t) {
-      Prim& p = prims[t];
+#pragma omp parallel for schedule(static) if (nt >= (size_t)kParallelBuildMin)
+    for (long t = 0; t < (long)nt; ++t) {
+      Prim& p = prims[(size_t)t];
       Box b;
-      for (int k = 0; k < 3; ++k) b.grow_pt(&m.pos[3 * (size_t)m.idx[3 * t + k]]);
+      for (int k = 0; k < 3; ++k) b.grow_pt(&m.pos[3 * (size_t)m.idx[3 * (size_t)t + k]]);
       for (int k = 0; k < 3; ++k) { p.lo[k] = b.lo[k]; p.hi[k] = b.hi[k]; p.c[k] = 0.5f * (b.lo[k] + b.hi[k]); }
       p.id = (uint32_t)t;
     }
@@ -220,10 +378,19 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     trees[mi].order.resize(nt);
     for (size_t t = 0; t < nt; ++t) trees[mi].order[t] = prims[t].id;
     trees[mi].built = true;
+  };
+  auto is_large = [&](size_t mi) { return scene.meshes[mi].idx.size() / 3 >= (size_t)kParallelBuildMin; };
+  for (size_t mi = 0; mi < n_mesh; ++mi)
+    if (used[mi] && !trees[mi].built && is_large(mi)) { build_mesh_tree(mi); scene.trees_built++; }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long mi = 0; mi < (long)n_mesh; ++mi) {
+    if (!used[mi] || trees[mi].built || is_large((size_t)mi)) continue;
+    build_mesh_tree((size_t)mi);
 #pragma omp atomic
     scene.trees_built++;
   }
 
+  lap("bottom trees");
   // nodes as they go into the blob: the binary trees, or their 4-wide collapse
   std::vector<std::vector<TreeNode>> emit(n_mesh);
   for (size_t mi = 0; mi < n_mesh; ++mi) {
@@ -276,6 +443,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     p.id = (uint32_t)k;
   }
   if (bad_xf) { err = "instance transform is singular"; return false; }
+  lap("instance world boxes");
   std::vector<TreeNode> top;
   int top_depth = 0;
   build_tree(iprims, kTopLeafSize, kTopBins, top, top_depth);
@@ -307,6 +475,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   const size_t o_tri = off;  off = align16(off + (size_t)16 * hdr.n_tris);
   const size_t o_inv = off;  off = align16(off + (size_t)64 * hdr.n_inst);
   const size_t o_meta = off; off = align16(off + (size_t)16 * hdr.n_inst);
+  lap("top tree");
   blob.assign(off, 0);
   std::memcpy(blob.data(), &hdr, sizeof hdr);
   if (!n_inst) return true;
@@ -371,6 +540,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     meta[4 * k + 2] = (int32_t)(n_top + trees[in.mesh].node_off);
     meta[4 * k + 3] = 0;
   }
+  lap("blob sections");
   return true;
 }
 

@@ -251,6 +251,34 @@ def test_c_abi_header_is_plain_c(tmp_path, product_lib):
     assert "c abi ok" in r.stdout
 
 
+def test_parallel_tree_build_is_deterministic(monkeypatch, product_lib):
+    """Meshes of 200 k triangles and more are built on several threads (upper levels with parallel passes over the
+    wide nodes, sub-trees as independent tasks, then renumbered): the blob is byte-identical to the single-thread
+    build, whatever the thread count."""
+    pos, nrm, idx = scenes.uv_sphere(1.0, 480, 240)
+    assert idx.shape[0] >= 200_000
+    g = np.random.default_rng(3)
+    pos = (pos + g.normal(scale=2e-3, size=pos.shape)).astype(np.float32)
+
+    def blob():
+        v = V3d_View(host_only=True)
+        m = v.AddMesh(pos, idx, nrm)
+        v.Display(m, None, 0)
+        v.Display(m, scenes.trsf((3, 0, 0), (0, 1, 0), 30.0), 0)
+        v.Update()
+        b = v.ExportBVH()
+        v.Remove()
+        return b
+
+    parallel = blob()
+    monkeypatch.setenv("CRT_BUILD_SERIAL", "1")
+    serial = blob()
+    assert parallel == serial
+    monkeypatch.delenv("CRT_BUILD_SERIAL")
+    monkeypatch.setenv("OMP_NUM_THREADS", "3")      # read by libgomp at load time only; the std::thread passes still vary
+    assert blob() == serial
+
+
 def test_recommit_after_edit_equals_fresh_build(product_lib):
     """Scene edits (SetLocation / material index) reuse the cached bottom trees; the resulting blob is the one a
     fresh build of the edited scene gives, and undoing the edit restores the original bytes."""
