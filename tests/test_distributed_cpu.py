@@ -81,3 +81,35 @@ def test_two_ranks_reproduce_single_process(tmp_path, product_lib, oracle_lib):
     single = o.render(40, 32, 7)
     assert np.array_equal(reduced[..., 3], single[..., 3])            # every pixel got all 7 samples
     assert np.allclose(reduced, single, rtol=2e-6, atol=1e-6)         # float summation order only
+
+
+def test_sample_partition_properties_randomised():
+    """sample_range / step_sample_start over random worlds and totals (hypothesis): the ranges tile [0, total)
+    exactly, in rank order, sizes differ by at most one; the weak-scaling schedule never hands a sample index to two
+    (step, rank) pairs."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(world=st.integers(1, 64), total=st.integers(0, 100_000))
+    def ranges(world, total):
+        spans = [D.sample_range(r, world, total) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+            assert f1 == f0 + c0
+        counts = [c for _, c in spans]
+        assert max(counts) - min(counts) <= 1 and counts == sorted(counts, reverse=True)
+
+    @settings(max_examples=100, deadline=None)
+    @given(world=st.integers(1, 16), spp=st.integers(1, 64), steps=st.integers(1, 20))
+    def schedule(world, spp, steps):
+        seen = set()
+        for s in range(steps):
+            for r in range(world):
+                first = D.step_sample_start(s, r, world, spp)
+                block = range(first, first + spp)
+                assert seen.isdisjoint(block)
+                seen.update(block)
+        assert seen == set(range(steps * world * spp))
+
+    ranges()
+    schedule()

@@ -520,3 +520,26 @@ def test_adaptive_render_is_a_prefix_of_the_plain_stream(oracle_lib):
         m = per_pixel == n
         assert np.array_equal(st["accum"][m], plain[m])
     o.close()
+
+
+def test_adaptive_allocation_randomised(oracle_lib):
+    """orc_adaptive_allocate under random error maps, budgets and wave indices (hypothesis): the prefix is monotone,
+    spends the budget exactly, respects the per-tile bound the seed table relies on, and a tile with a larger error
+    estimate never receives fewer samples than one with a smaller estimate by more than the rounding step."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import oracle_ffi
+
+    @settings(max_examples=150, deadline=None)
+    @given(errs=st.lists(st.integers(0, 4_194_304), min_size=1, max_size=300), budget=st.integers(1, 50_000),
+           wave=st.integers(0, 2**31))
+    def check(errs, budget, wave):
+        err = np.array(errs, dtype=np.uint32)
+        cum = oracle_ffi.adaptive_allocate(err, budget, wave).astype(np.int64)
+        k = np.diff(cum)
+        assert cum[0] >= 0 and (k >= 0).all() and cum[-1] == budget
+        assert k.max() <= 32 * budget // err.size + 1
+        order = np.argsort(err, kind="stable")
+        ks = k[order]
+        assert (np.diff(ks) >= -1).all()      # systematic sampling: monotone in the weight up to one sample
+
+    check()
