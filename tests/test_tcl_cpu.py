@@ -324,3 +324,31 @@ def test_named_materials_against_the_reference_icons(oracle_lib):
         a, b = ours[n], ref[n]
         assert a[0] > a[1] > a[2] and b[0] > b[1] > b[2]
         assert abs(a[1] / a[0] - b[1] / b[0]) < 0.2, (n, a, b)
+
+
+def test_png_reader_against_pillow(tmp_path):
+    """imageio.read_png_rgb8 (used for `rttexture` images and the reference's material icons) decodes what Pillow
+    writes: RGB, RGBA, grey, grey + alpha and palette images, with adaptive scanline filters."""
+    PIL = pytest.importorskip("PIL.Image")
+    g = np.random.default_rng(9)
+    yy, xx = np.mgrid[0:37, 0:53]
+    smooth = np.stack([(xx * 4) % 256, (yy * 6) % 256, (xx + yy) * 2 % 256], axis=2).astype(np.uint8)   # exercises Sub/Up/Paeth
+    noise = g.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    for name, arr in (("smooth", smooth), ("noise", noise)):
+        for mode in ("RGB", "RGBA", "L", "LA", "P"):
+            img = PIL.fromarray(arr, "RGB")
+            if mode == "RGBA":
+                img.putalpha(PIL.fromarray(g.integers(0, 256, size=(37, 53), dtype=np.uint8), "L"))
+            elif mode in ("L", "LA", "P"):
+                img = img.convert(mode)
+            path = tmp_path / f"{name}_{mode}.png"
+            img.save(path, optimize=True)
+            want = np.asarray(PIL.open(path).convert("RGB"))
+            got = imageio.read_png_rgb8(str(path))
+            assert got.shape == want.shape and np.array_equal(got, want), (name, mode)
+    # and our own writer round-trips (bottom-up in, top-down out)
+    imageio.write_png(str(tmp_path / "own.png"), noise[::-1])
+    assert np.array_equal(imageio.read_png_rgb8(str(tmp_path / "own.png")), noise)
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.png").write_bytes(b"not a png")
+        imageio.read_png_rgb8(str(tmp_path / "bad.png"))
