@@ -595,3 +595,25 @@ def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracl
     for k in ("rays_nearest", "rays_any", "n_inner", "n_tri", "n_inner_any", "n_tri_any", "shaded_hits", "samples"):
         assert st[k] == ost[k], (knob, k)
     view.Remove()
+
+
+def test_regression_harness_end_to_end(tmp_path, product_lib):
+    """`python -m cadrays_b200.regress` (the contract of the reference's testing/CADRays_Testing.py) with the real
+    runner: two runs of the same script are pixel-identical, so after `-u` the difference mask is empty."""
+    from cadrays_b200 import regress
+    from tests.test_tcl_cpu import SCRIPT
+    scripts = tmp_path / "scripts"; scripts.mkdir()
+    model = tmp_path / "template"; model.mkdir()
+    (scripts / "Scene.tcl").write_text(SCRIPT)
+    runner = lambda script, frames, out_dir: __import__("cadrays_b200.run", fromlist=["main"]).main(
+        [script, str(frames), "--out", out_dir, "--size", "96x64", "--spp-per-redraw", "4"])
+    first = regress.run_folder(str(scripts), 8, str(tmp_path), str(model), runner=runner)
+    assert os.path.isfile(os.path.join(first, "Output_Scene_8.png"))
+    assert regress.main(["-o", str(tmp_path), "-m", str(model), "-u"]) == 0
+    import time
+    time.sleep(1.1)                       # run folders are named to the second
+    second = regress.run_folder(str(scripts), 8, str(tmp_path), str(model), runner=runner)
+    assert second != first
+    report = open(os.path.join(second, "Result.html"), encoding="utf-8").read()
+    assert "identical" in report and "pixels differ" not in report
+    assert "Scene.tcl" in regress.read_rates(os.path.join(second, "Result.html"))

@@ -352,3 +352,45 @@ def test_png_reader_against_pillow(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "bad.png").write_bytes(b"not a png")
         imageio.read_png_rgb8(str(tmp_path / "bad.png"))
+
+
+def test_regression_harness_bookkeeping(tmp_path):
+    """cadrays_b200.regress keeps the contract of testing/CADRays_Testing.py: run every script for N frames, collect
+    Output_<script>_<N>.png/.txt into a dated folder, report frame rates against the template (flagging changes above
+    -d percent) and a difference mask per image; -u promotes the newest run to the template.  The renderer is
+    injected here (no GPU): a fake runner writes the two files the real one writes."""
+    from datetime import datetime
+    from cadrays_b200 import regress
+    scripts = tmp_path / "scripts"; scripts.mkdir()
+    model = tmp_path / "template"; model.mkdir()
+    out = tmp_path / "out"; out.mkdir()
+    for name in ("A.tcl", "B.tcl", "notes.txt"):
+        (scripts / name).write_text("# scene\n")
+    shade = {"A": 10, "B": 200}
+    fps = {"A": 100.0, "B": 50.0}
+
+    def fake_runner(script, frames, out_dir):
+        stem = os.path.splitext(os.path.basename(script))[0]
+        img = np.full((8, 12, 3), shade[stem], np.uint8)
+        imageio.write_png(os.path.join(out_dir, f"Output_{stem}_{frames}.png"), img)
+        with open(os.path.join(out_dir, f"Output_{stem}_{frames}.txt"), "w") as f:
+            f.write(f"{fps[stem]:.3f}\n")
+
+    first = regress.run_folder(str(scripts), 7, str(out), str(model), runner=fake_runner, now=datetime(2026, 1, 2, 3, 4, 5))
+    assert os.path.basename(first) == "02_01_2026 03_04_05"
+    assert sorted(os.listdir(first)) == ["Output_A_7.png", "Output_B_7.png", "Result.html"]      # .txt consumed, no template yet
+    assert regress.read_rates(os.path.join(first, "Result.html")) == {"A.tcl": 100.0, "B.tcl": 50.0}
+    assert regress.main(["-o", str(out), "-m", str(model), "-u"]) == 0
+    assert sorted(os.listdir(model)) == ["A.png", "B.png", "Result.html"]
+    # second run: A unchanged, B renders differently and 10 % slower
+    shade["B"], fps["B"] = 201, 45.0
+    second = regress.run_folder(str(scripts), 7, str(out), str(model), max_diff=2.0, runner=fake_runner, now=datetime(2026, 1, 2, 4, 0, 0))
+    report = open(os.path.join(second, "Result.html"), encoding="utf-8").read()
+    assert "identical" in report and "96 pixels differ" in report
+    assert "background-color:red" in report and "[-10.0000%]" in report and "[+0.0000%]" in report
+    assert imageio.read_png_rgb8(os.path.join(second, "Diff_B.png")).min() == 255
+    assert imageio.read_png_rgb8(os.path.join(second, "Diff_A.png")).max() == 0
+    assert regress.newest_run(str(out)) == second
+    # argument errors follow the reference: exit code 2
+    assert regress.main(["-i", str(scripts), "-m", str(tmp_path / "missing")]) == 2
+    assert regress.main(["-m", str(model), "-u"]) == 2
