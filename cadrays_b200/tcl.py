@@ -20,6 +20,7 @@ from __future__ import annotations
 import ast
 import math
 import operator
+import re
 import os
 from typing import Callable, Dict, List, Optional
 
@@ -32,6 +33,20 @@ from .view import (Graphic3d_BSDF, Graphic3d_Camera, Graphic3d_Fresnel, Graphic3
 
 class TclError(RuntimeError):
     pass
+
+
+class _Break(Exception):
+    pass
+
+
+class _Continue(Exception):
+    pass
+
+
+class _Return(Exception):
+    def __init__(self, value=""):
+        super().__init__(value)
+        self.value = value
 
 
 # ------------------------------------------------------------------ named materials (re-derived)
@@ -106,13 +121,27 @@ _FUN = {"sin": math.sin, "cos": math.cos, "tan": math.tan, "sqrt": math.sqrt, "a
 def tcl_expr(text: str):
     """Tcl `expr` for the arithmetic the scripts use (C operators, integer division, math functions)."""
     src = text.replace("&&", " and ").replace("||", " or ").replace("!", " not ").replace(" not =", "!=")
-    tree = ast.parse(src.strip(), mode="eval")
+    src = re.sub(r"\beq\b", "==", re.sub(r"\bne\b", "!=", src))          # string comparison operators
+    try:
+        tree = ast.parse(src.strip(), mode="eval")
+    except SyntaxError:
+        raise TclError(f"expr: syntax error in '{text}'")
+
+    def same_kind(a, b):
+        # Tcl compares numerically when both operands are numbers, else as strings
+        if isinstance(a, str) or isinstance(b, str):
+            return str(a) if not isinstance(a, str) else a, str(b) if not isinstance(b, str) else b
+        return a, b
 
     def ev(n):
         if isinstance(n, ast.Expression):
             return ev(n.body)
         if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)):
             return n.value
+        if isinstance(n, ast.Constant) and isinstance(n.value, str):
+            return n.value
+        if isinstance(n, ast.Name):              # a substituted variable that held a word: a string operand
+            return n.id
         if isinstance(n, ast.BinOp):
             a, b = ev(n.left), ev(n.right)
             if isinstance(n.op, ast.Div):
@@ -132,7 +161,7 @@ def tcl_expr(text: str):
             vals = [ev(v) for v in n.values]
             return int(all(vals)) if isinstance(n.op, ast.And) else int(any(vals))
         if isinstance(n, ast.Compare) and len(n.ops) == 1:
-            return int(_CMP[type(n.ops[0])](ev(n.left), ev(n.comparators[0])))
+            return int(_CMP[type(n.ops[0])](*same_kind(ev(n.left), ev(n.comparators[0]))))
         if isinstance(n, ast.IfExp):
             return ev(n.body) if ev(n.test) else ev(n.orelse)
         if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id in _FUN:
@@ -149,6 +178,35 @@ def _fmt(v) -> str:
     return str(v)
 
 
+class _Linked(dict):
+    """A proc's variable table in which some names are links to the global table (`global name`)."""
+
+    def __init__(self, local, globals_, name):
+        super().__init__(local)
+        self._g = globals_
+        self._names = set(getattr(local, "_names", ())) | {name}
+        for nm in self._names:
+            super().pop(nm, None)
+
+    def __contains__(self, k):
+        return (k in self._names and k in self._g) or super().__contains__(k)
+
+    def __getitem__(self, k):
+        return self._g[k] if k in self._names else super().__getitem__(k)
+
+    def __setitem__(self, k, v):
+        if k in self._names:
+            self._g[k] = v
+        else:
+            super().__setitem__(k, v)
+
+    def get(self, k, default=None):
+        return self._g.get(k, default) if k in self._names else super().get(k, default)
+
+    def pop(self, k, *default):
+        return self._g.pop(k, *default) if k in self._names else super().pop(k, *default)
+
+
 class Interp:
     """Draw_Interpretor stand-in: command table + variables."""
 
@@ -159,8 +217,11 @@ class Interp:
         self.strict = False
         self.output: List[str] = []
         for name in ("set", "expr", "for", "if", "incr", "eval", "lrepeat", "puts", "list", "llength", "lindex", "foreach",
-                     "while", "catch", "unset", "append", "string"):
+                     "while", "catch", "unset", "append", "string", "proc", "return", "break", "continue", "global",
+                     "lappend", "lrange", "concat", "join", "split", "format", "info"):
             self.cmds[name] = getattr(self, "_c_" + name)
+        self._frames: List[Dict[str, str]] = []      # saved variable tables of the callers while a proc body runs
+        self._globals: Dict[str, str] = self.vars
 
     # -- parsing
     def eval(self, script: str) -> str:
@@ -310,7 +371,12 @@ class Interp:
         self.eval(init)
         guard = 0
         while self._cond(cond):
-            self.eval(body)
+            try:
+                self.eval(body)
+            except _Break:
+                break
+            except _Continue:
+                pass
             self.eval(step)
             guard += 1
             if guard > 10_000_000:
@@ -319,16 +385,29 @@ class Interp:
     def _c_while(self, a):
         guard = 0
         while self._cond(a[0]):
-            self.eval(a[1])
+            try:
+                self.eval(a[1])
+            except _Break:
+                break
+            except _Continue:
+                pass
             guard += 1
             if guard > 10_000_000:
                 raise TclError("while: runaway loop")
 
     def _c_foreach(self, a):
         var, items, body = a
-        for it in self._split_list(items):
-            self.vars[var] = it
-            self.eval(body)
+        names = self._split_list(var)
+        values = self._split_list(items)
+        for k in range(0, len(values), max(1, len(names))):
+            for j, nm in enumerate(names):
+                self.vars[nm] = values[k + j] if k + j < len(values) else ""
+            try:
+                self.eval(body)
+            except _Break:
+                break
+            except _Continue:
+                continue
 
     def _c_if(self, a):
         i = 0
@@ -352,12 +431,111 @@ class Interp:
     def _c_eval(self, a):
         return self.eval(" ".join(a))
 
+    # -- procedures: one variable table per call, `global` links names to the outermost table
+    def _c_proc(self, a):
+        name, params, body = a
+        spec = [self._split_list(p) for p in self._split_list(params)]
+
+        def call(args, _spec=spec, _body=body, _name=name):
+            local: Dict[str, str] = {}
+            rest = list(args)
+            for k, p in enumerate(_spec):
+                if p[0] == "args" and k == len(_spec) - 1:
+                    local["args"] = self._join_list(rest)
+                    rest = []
+                elif rest:
+                    local[p[0]] = rest.pop(0)
+                elif len(p) > 1:
+                    local[p[0]] = p[1]
+                else:
+                    raise TclError(f'wrong # args: should be "{_name} {params}"')
+            if rest:
+                raise TclError(f'wrong # args: should be "{_name} {params}"')
+            self._frames.append(self.vars)
+            self.vars = local
+            try:
+                return self.eval(_body)
+            except _Return as r:
+                return r.value
+            finally:
+                self.vars = self._frames.pop()
+
+        self.cmds[name] = call
+        return ""
+
+    def _c_return(self, a):
+        raise _Return(a[-1] if a else "")
+
+    def _c_break(self, a):
+        raise _Break()
+
+    def _c_continue(self, a):
+        raise _Continue()
+
+    def _c_global(self, a):
+        if self.vars is self._globals:
+            return ""
+        for nm in a:
+            self.vars = _Linked(self.vars, self._globals, nm)
+        return ""
+
+    def _c_lappend(self, a):
+        items = self._split_list(self.vars.get(a[0], "")) + list(a[1:])
+        self.vars[a[0]] = self._join_list(items)
+        return self.vars[a[0]]
+
+    def _c_lrange(self, a):
+        items = self._split_list(a[0])
+        idx = lambda t: len(items) - 1 + (int(t[3:]) if t[3:4] in ("-", "+") else 0) if t.startswith("end") else int(t)
+        return self._join_list(items[max(0, idx(a[1])):idx(a[2]) + 1])
+
+    def _c_concat(self, a):
+        return " ".join(x.strip() for x in a if x.strip())
+
+    def _c_join(self, a):
+        return (a[1] if len(a) > 1 else " ").join(self._split_list(a[0]))
+
+    def _c_split(self, a):
+        seps = a[1] if len(a) > 1 else " \t\n"
+        out, cur = [], ""
+        for ch in a[0]:
+            if ch in seps:
+                out.append(cur); cur = ""
+            else:
+                cur += ch
+        out.append(cur)
+        return self._join_list(out)
+
+    def _c_format(self, a):
+        vals = []
+        for v in a[1:]:
+            try:
+                vals.append(int(v))
+            except ValueError:
+                try:
+                    vals.append(float(v))
+                except ValueError:
+                    vals.append(v)
+        try:
+            return a[0] % tuple(vals)
+        except (TypeError, ValueError) as e:
+            raise TclError(f"format: {e}")
+
+    def _c_info(self, a):
+        if a and a[0] == "exists":
+            return "1" if a[1] in self.vars else "0"
+        if a and a[0] in ("commands", "procs"):
+            return self._join_list(sorted(self.cmds))
+        raise TclError("info: unsupported subcommand " + (a[0] if a else ""))
+
     def _c_catch(self, a):
         try:
             r = self.eval(a[0])
             if len(a) > 1:
                 self.vars[a[1]] = r
             return "0"
+        except (_Break, _Continue, _Return):
+            raise
         except Exception as e:  # noqa: BLE001
             if len(a) > 1:
                 self.vars[a[1]] = str(e)

@@ -394,3 +394,49 @@ def test_regression_harness_bookkeeping(tmp_path):
     # argument errors follow the reference: exit code 2
     assert regress.main(["-i", str(scripts), "-m", str(tmp_path / "missing")]) == 2
     assert regress.main(["-m", str(model), "-u"]) == 2
+
+
+def test_tcl_procedures_and_control_flow():
+    """The evaluator beyond straight-line scripts: proc with defaults / args / recursion, global, return, break,
+    continue, multi-variable foreach, lappend / lrange / join / split / concat, format, info exists, string
+    comparison in expr -- what hand-written scene scripts use around the DRAW commands."""
+    it = tcl.Interp()
+    it.strict = True
+    it.eval("""
+set total 0
+proc add {a {b 10} args} { global total; set total [expr $total + $a + $b + [llength $args]]; return [expr $a + $b] }
+set r1 [add 1]
+set r2 [add 1 2 x y z]
+set acc {}
+foreach {k v} {a 1 b 2 c 3} { if {$k == "b"} { continue }; lappend acc $k$v }
+set n 0
+while {1} { incr n; if {$n >= 5} { break } }
+for {set i 0} {$i < 10} {incr i} { if {$i == 3} { break } }
+set f [format "%03d-%.2f-%s" 7 3.14159 hi]
+set lr [lrange {a b c d e} 1 end-1]
+proc fact {n} { if {$n <= 1} { return 1 }; return [expr $n * [fact [expr $n - 1]]] }
+set f5 [fact 5]
+set same [expr {"abc" eq "abc"}]
+set diff [expr {"abc" ne "abd"}]
+set j [join {a b c} -]
+set sp [split a,b,c ,]
+set cc [concat {a b} c {d e}]
+""")
+    v = it.vars
+    assert (v["total"], v["r1"], v["r2"]) == ("17", "11", "3")
+    assert v["acc"] == "a1 c3" and v["n"] == "5" and v["i"] == "3"
+    assert v["f"] == "007-3.14-hi" and v["lr"] == "b c d" and v["f5"] == "120"
+    assert v["same"] == "1" and v["diff"] == "1" and v["j"] == "a-b-c" and v["sp"] == "a b c" and v["cc"] == "a b c d e"
+    assert it.eval("info exists total") == "1" and it.eval("info exists missing") == "0"
+    assert "a" not in v and "b" not in v                     # proc locals do not leak
+    with pytest.raises(tcl.TclError):
+        it.eval("add")                                        # wrong # args
+    # a proc that places objects: DRAW commands work inside procedures
+    s = tcl.DrawSession(64, 48)
+    s.strict = True
+    s.eval("""
+proc ball {name x y z mat} { psphere $name 0.2; vdisplay $name; vsetlocation $name $x $y $z; vsetmaterial $name $mat }
+foreach {n x m} {s1 0 gold s2 1 jade s3 2 glass} { ball $n $x 0 0 $m }
+""")
+    d = s.scene()
+    assert len(d.instances) == 3 and [round(float(xf[0, 3])) for _, xf, _ in d.instances] == [0, 1, 2]
