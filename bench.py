@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--parts", type=int, default=1000)
     ap.add_argument("--tris", type=int, default=1_000_000)
-    ap.add_argument("--workload", default="assembly", choices=["assembly", "cornell", "materials", "instanced", "instanced_flat"])
+    ap.add_argument("--workload", default="assembly", choices=["assembly", "cornell", "materials", "product_shot", "instanced", "instanced_flat"])
     ap.add_argument("--bvh-width", type=int, default=2, choices=[2, 4], help="2 = binary BVH (default), 4 = OCCT's optional QUAD_BVH collapse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="1920x1080x32",
@@ -61,6 +61,9 @@ def make_scene(args):
         return scenes.cornell_box(args.width, args.height, depth=args.depth)
     if args.workload == "materials":
         return scenes.materials_scene(args.width, args.height, depth=args.depth)
+    if args.workload == "product_shot":        # C4 geometry and lighting (environment only); pass --width 3840 --height 2160 --depth 12 --spp 4
+        d = scenes.product_shot(args.width, args.height, depth=args.depth)
+        return d
     if args.workload == "instanced_flat":      # C5, flattened variant: every instance owns its geometry (10.5 M unique triangles)
         return scenes.instanced(n_meshes=1024, width=args.width, height=args.height, depth=args.depth)
     return scenes.instanced(width=args.width, height=args.height, depth=args.depth)
