@@ -424,7 +424,7 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
 
     // ---- inner nodes.  CRT_INNER_EXIT = N > 1: lanes leave the loop once fewer than N lanes are still
     // walking inner nodes while another lane of the warp waits for its leaf / instance step (the
-    // simulator tools/simt_model.py predicts fewer issue slots per ray for N around 12).
+    // simulator tests/analysis/simt_model.py predicts fewer issue slots per ray for N around 12).
     while (cur >= 0) {
       if (!QUAD) {
         if (COUNT) { if (any_ray) { cnt.n_inner_any++; cnt.n_boxes_any += 2; } else { cnt.n_inner++; cnt.n_boxes += 2; } }

@@ -444,7 +444,7 @@ static inline v3 xf_vector(const float* m, v3 p)
            fmaf(m[10], p.z, fmaf(m[9], p.y, m[8] * p.x)));
 }
 
-/* optional per-ray event recorder (analysis tooling: feeds tools/simt_model.py) */
+/* optional per-ray event recorder (analysis tooling: feeds tests/analysis/simt_model.py) */
 static __thread uint8_t* g_ev = NULL;
 static __thread int g_ev_n = 0, g_ev_cap = 0;
 #define ORC_EVENT(code) do { if (g_ev && g_ev_n < g_ev_cap) g_ev[g_ev_n++] = (uint8_t)(code); } while (0)

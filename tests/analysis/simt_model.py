@@ -1,11 +1,14 @@
 """Offline SIMT cost model of traversal control-flow strategies (analysis tooling, CPU only).
 
+Lives under tests/ because it drives the CPU oracle (`orc_trace_events`), and the oracle is test infrastructure: nothing
+outside tests/, smoke() and the CPU legs of bench.py may touch it.
+
 Takes real per-ray traversal event strings from the oracle (1 = inner node, 2 = instance switch,
 3+k = leaf with k triangles) for a scene, groups rays into 32-lane warps with per-lane refill, and
 counts warp-level instruction issue for several loop structures.  Instruction costs per step come
 from the SASS of the current kernels.  Used to decide what is worth building before spending GPU time.
 
-  python tools/simt_model.py [--rays 65536] [--scene assembly]
+  python tests/analysis/simt_model.py [--rays 65536] [--scene assembly]
 """
 import argparse
 import ctypes as C
@@ -14,7 +17,7 @@ from pathlib import Path
 
 import numpy as np
 
-REPO = Path(__file__).resolve().parent.parent
+REPO = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(REPO))
 
 C_N, C_S, C_L0, C_T, C_R = 50, 100, 15, 45, 40
