@@ -61,11 +61,17 @@ def test_product_never_imports_the_oracle():
     bad = re.compile(r"(#\s*include[^\n]*oracle|^\s*(from|import)\s+oracle|oracle_ffi|libcadrays_oracle|dlopen)", re.M)
     files = list((REPO / "cadrays_b200").rglob("*.py")) + [p for p in (REPO / "cadrays_b200" / "csrc").glob("*") if p.is_file()]
     files.append(REPO / "include" / "cadrays_b200.h")
+    files.append(REPO / "include" / "cadrays_b200.hpp")
+    files += [p for p in (REPO / "tools").glob("*") if p.is_file()]      # measurement tooling drives the product only
     for p in files:
         m = bad.search(p.read_text(errors="ignore"))
         assert m is None, (p, m.group(0))
     from cadrays_b200 import build
     assert not any("oracle" in str(x) for x in build._sources())
+    # bench.py and __graft_entry__.py may use the oracle, but only in the CPU legs / smoke(): never at import time
+    for name in ("bench.py", "__graft_entry__.py"):
+        top_level = [ln for ln in (REPO / name).read_text().splitlines() if re.match(r"^(from|import)\s+oracle", ln)]
+        assert not top_level, (name, top_level)
 
 
 def _parse_blob(blob):
