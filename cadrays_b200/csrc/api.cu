@@ -801,6 +801,7 @@ int crt_scene_clear(crt_context* c)
   c->scene.meshes.clear();
   c->scene.instances.clear();
   c->scene.tree_cache.clear();
+  c->scene.blob_signature.clear();      // new meshes may reuse ids and sizes: the next blob is written in full
   c->geometry_dirty = true;
   return CRT_OK;
 }
@@ -1189,6 +1190,7 @@ int crt_bvh_import(crt_context* c, const void* buf, size_t size)
   if (rc) return rc;
   std::vector<uint8_t> keep(static_cast<const uint8_t*>(buf), static_cast<const uint8_t*>(buf) + size);
   c->blob.swap(keep);
+  c->scene.blob_signature.clear();      // the blob no longer comes from this context's scene
   rc = load_blob(c);
   if (rc) { c->blob.swap(keep); return rc; }
   c->geometry_dirty = false;

@@ -382,7 +382,9 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   auto is_large = [&](size_t mi) { return scene.meshes[mi].idx.size() / 3 >= (size_t)kParallelBuildMin; };
   for (size_t mi = 0; mi < n_mesh; ++mi)
     if (used[mi] && !trees[mi].built && is_large(mi)) { build_mesh_tree(mi); scene.trees_built++; }
-#pragma omp parallel for schedule(dynamic, 1)
+  bool any_small = false;
+  for (size_t mi = 0; mi < n_mesh; ++mi) any_small = any_small || (used[mi] && !trees[mi].built && !is_large(mi));
+#pragma omp parallel for schedule(dynamic, 1) if (any_small)
   for (long mi = 0; mi < (long)n_mesh; ++mi) {
     if (!used[mi] || trees[mi].built || is_large((size_t)mi)) continue;
     build_mesh_tree((size_t)mi);
@@ -427,13 +429,20 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     if (!invert_affine(in.xf, &inv[16 * k])) { bad_xf = true; continue; }
     const Mesh& m = scene.meshes[in.mesh];
     Box b;
-    const size_t nv = m.pos.size() / 3;
-    for (size_t v = 0; v < nv; ++v) {
-      const float* p = &m.pos[3 * v];
-      float q[3];
-      for (int r = 0; r < 3; ++r)
-        q[r] = in.xf[4 * r] * p[0] + in.xf[4 * r + 1] * p[1] + in.xf[4 * r + 2] * p[2] + in.xf[4 * r + 3];
-      b.grow_pt(q);
+    if (in.box_valid && in.box_mesh == in.mesh && std::memcmp(in.box_xf, in.xf, sizeof in.xf) == 0) {
+      std::memcpy(b.lo, in.box_lo, 12); std::memcpy(b.hi, in.box_hi, 12);
+    } else {
+      const size_t nv = m.pos.size() / 3;
+      for (size_t v = 0; v < nv; ++v) {
+        const float* p = &m.pos[3 * v];
+        float q[3];
+        for (int r = 0; r < 3; ++r)
+          q[r] = in.xf[4 * r] * p[0] + in.xf[4 * r + 1] * p[1] + in.xf[4 * r + 2] * p[2] + in.xf[4 * r + 3];
+        b.grow_pt(q);
+      }
+      std::memcpy(in.box_lo, b.lo, 12); std::memcpy(in.box_hi, b.hi, 12);
+      std::memcpy(in.box_xf, in.xf, sizeof in.xf);
+      in.box_mesh = in.mesh; in.box_valid = true;
     }
     Prim& p = iprims[k];
     for (int r = 0; r < 3; ++r) {
@@ -476,7 +485,25 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   const size_t o_inv = off;  off = align16(off + (size_t)64 * hdr.n_inst);
   const size_t o_meta = off; off = align16(off + (size_t)16 * hdr.n_inst);
   lap("top tree");
-  blob.assign(off, 0);
+  // same meshes, same instance -> mesh map, same tree shapes as the blob the caller still holds?
+  std::vector<uint64_t> sig;
+  sig.reserve(8 + 4 * n_mesh + n_inst);
+  sig.push_back(quad); sig.push_back(n_top); sig.push_back(off); sig.push_back(any_uv);
+  for (size_t mi = 0; mi < n_mesh; ++mi)
+    if (used[mi]) {
+      sig.push_back(mi); sig.push_back(scene.meshes[mi].pos.size()); sig.push_back(scene.meshes[mi].idx.size());
+      sig.push_back(mesh_nodes(mi).size());
+    }
+  sig.push_back(~0ull);
+  for (const Instance& in : scene.instances) sig.push_back(in.mesh);
+  BlobHeader old_hdr{};
+  if (blob.size() >= sizeof old_hdr) std::memcpy(&old_hdr, blob.data(), sizeof old_hdr);
+  const bool patch = n_inst && blob.size() == off && sig == scene.blob_signature && old_hdr.magic == kBlobMagic &&
+                     old_hdr.n_nodes == hdr.n_nodes && old_hdr.n_verts == hdr.n_verts && old_hdr.n_tris == hdr.n_tris &&
+                     old_hdr.n_inst == hdr.n_inst && old_hdr.n_top_nodes == hdr.n_top_nodes && old_hdr.flags == hdr.flags &&
+                     std::getenv("CRT_BLOB_NO_PATCH") == nullptr;
+  if (!patch) blob.assign(off, 0);
+  scene.blob_signature = n_inst ? sig : std::vector<uint64_t>{};
   std::memcpy(blob.data(), &hdr, sizeof hdr);
   if (!n_inst) return true;
 
@@ -507,7 +534,8 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
       info[4 * n + 0] = 0; info[4 * n + 1] = t.a; info[4 * n + 2] = t.b; info[4 * n + 3] = 0;
     }
   }
-  for (size_t mi = 0; mi < n_mesh; ++mi) {
+  if (patch) scene.blobs_patched++;
+  for (size_t mi = 0; mi < n_mesh && !patch; ++mi) {
     if (!used[mi]) continue;
     const MeshTree& mt = trees[mi];
     const Mesh& m = scene.meshes[mi];

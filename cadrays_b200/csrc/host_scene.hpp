@@ -25,6 +25,12 @@ struct Instance {
   uint32_t mesh;
   uint32_t material;
   float    xf[12];             // row-major 3x4 object -> world
+  // world box of the transformed vertices, kept with the transform and mesh it was computed for: a commit after
+  // one object moved transforms the vertices of that object only
+  mutable bool     box_valid = false;
+  mutable uint32_t box_mesh = 0;
+  mutable float    box_xf[12] = { 0 };
+  mutable float    box_lo[3] = { 0 }, box_hi[3] = { 0 };
 };
 
 // Bottom-level tree of one mesh, kept across commits: moving an object or changing its material
@@ -47,6 +53,12 @@ struct HostScene {
   std::vector<Instance> instances;
   mutable std::vector<BottomTree> tree_cache;   // parallel to meshes
   mutable uint64_t trees_built = 0;             // statistics: bottom trees built so far
+  // what the mesh sections of the last blob were built from (mesh ids and sizes, instance -> mesh map, tree
+  // width, top-level node count): when an edit only moves instances or changes their materials, build_blob
+  // rewrites the header, the top-level nodes and the instance records of the caller's blob and leaves the
+  // vertex / triangle / bottom-node sections (almost all of its bytes) alone
+  mutable std::vector<uint64_t> blob_signature;
+  mutable uint64_t blobs_patched = 0;           // statistics: how often that shortcut was taken
 };
 
 // "CRTB" blob, version 1 -- layout documented in DESIGN.md.  64-byte header

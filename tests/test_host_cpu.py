@@ -257,6 +257,49 @@ def test_c_abi_header_is_plain_c(tmp_path, product_lib):
     assert "c abi ok" in r.stdout
 
 
+def test_blob_patch_shortcut_never_keeps_stale_geometry(product_lib):
+    """A commit after instance-only edits rewrites just the header, the top-level nodes and the instance records of
+    the previous blob.  It must not survive anything that changes geometry: Clear() followed by a different mesh
+    with the same counts, another instance -> mesh map, or a change of tree width."""
+    def fresh(meshes, inst, width=2):
+        v = V3d_View(host_only=True)
+        p = Graphic3d_RenderingParams(BvhWidth=width)
+        v.SetRenderingParams(p)
+        ids = [v.AddMesh(*m) for m in meshes]
+        for m, xf in inst:
+            v.Display(ids[m], xf, 0)
+        v.Update()
+        b = v.ExportBVH()
+        v.Remove()
+        return b
+
+    pa, na, ia = scenes.uv_sphere(1.0, 24, 12)
+    pb = (pa * np.array([1.0, 2.0, 0.5], np.float32)).astype(np.float32)          # same counts, other shape
+    sphere_a, sphere_b = (pa, ia, na), (pb, ia, na)
+    move = scenes.trsf((2, 0, 0))
+    v = V3d_View(host_only=True)
+    a = v.AddMesh(*sphere_a)
+    v.Display(a, None, 0); v.Display(a, move, 0)
+    v.Update()
+    assert v.ExportBVH() == fresh([sphere_a], [(0, None), (0, move)])
+    v.SetLocation(1, scenes.trsf((0, 3, 0)))                                        # shortcut applies
+    v.Update()
+    assert v.ExportBVH() == fresh([sphere_a], [(0, None), (0, scenes.trsf((0, 3, 0)))])
+    v.Clear()                                                                       # same ids and sizes, other vertices
+    b = v.AddMesh(*sphere_b)
+    v.Display(b, None, 0); v.Display(b, scenes.trsf((0, 3, 0)), 0)
+    v.Update()
+    assert v.ExportBVH() == fresh([sphere_b], [(0, None), (0, scenes.trsf((0, 3, 0)))])
+    c = v.AddMesh(*sphere_a)                                                        # second mesh, map changes
+    v.Display(c, move, 0)
+    v.Update()
+    assert v.ExportBVH() == fresh([sphere_b, sphere_a], [(0, None), (0, scenes.trsf((0, 3, 0))), (1, move)])
+    p = v.ChangeRenderingParams(); p.BvhWidth = 4                                   # tree width changes
+    v.SetRenderingParams(p); v.Update()
+    assert v.ExportBVH() == fresh([sphere_b, sphere_a], [(0, None), (0, scenes.trsf((0, 3, 0))), (1, move)], width=4)
+    v.Remove()
+
+
 def test_parallel_tree_build_is_deterministic(monkeypatch, product_lib):
     """Meshes of 200 k triangles and more are built on several threads (upper levels with parallel passes over the
     wide nodes, sub-trees as independent tasks, then renumbered): the blob is byte-identical to the single-thread
