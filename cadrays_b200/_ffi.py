@@ -79,6 +79,7 @@ PROTOTYPES = {
     "crt_instance_add": (C.c_int, [_ctx, C.c_uint32, _f, C.c_uint32, _u32]),
     "crt_instance_set_transform": (C.c_int, [_ctx, C.c_uint32, _f]),
     "crt_instance_set_material": (C.c_int, [_ctx, C.c_uint32, C.c_uint32]),
+    "crt_instance_set_visible": (C.c_int, [_ctx, C.c_uint32, C.c_int]),
     "crt_scene_clear": (C.c_int, [_ctx]),
     "crt_materials_set": (C.c_int, [_ctx, C.POINTER(crt_bsdf), C.c_uint32]),
     "crt_texture_create": (C.c_int, [_ctx, _u8, C.c_uint32, C.c_uint32, _u32]),

@@ -795,6 +795,17 @@ int crt_instance_set_material(crt_context* c, uint32_t inst, uint32_t material_i
   return CRT_OK;
 }
 
+int crt_instance_set_visible(crt_context* c, uint32_t inst, int visible)
+{
+  CRT_REQUIRE(c, "null context");
+  CRT_REQUIRE(inst < c->scene.instances.size(), "unknown instance id");
+  if (c->scene.instances[inst].visible != (visible != 0)) {
+    c->scene.instances[inst].visible = visible != 0;
+    c->geometry_dirty = true;
+  }
+  return CRT_OK;
+}
+
 int crt_scene_clear(crt_context* c)
 {
   CRT_REQUIRE(c, "null context");

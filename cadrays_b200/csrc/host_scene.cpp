@@ -351,7 +351,9 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
 
   const bool quad = bvh_width == 4;
   const size_t n_mesh = scene.meshes.size();
-  const size_t n_inst = scene.instances.size();
+  bool any_visible = false;
+  for (const Instance& in : scene.instances) any_visible = any_visible || in.visible;
+  const size_t n_inst = any_visible ? scene.instances.size() : 0;   // nothing displayed = an empty scene
   scene.tree_cache.resize(n_mesh);
   std::vector<MeshTree>& trees = scene.tree_cache;
   std::vector<char> used(n_mesh, 0);
@@ -452,6 +454,12 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     p.id = (uint32_t)k;
   }
   if (bad_xf) { err = "instance transform is singular"; return false; }
+  {   // the top-level tree is built over the displayed instances only
+    size_t n_vis = 0;
+    for (size_t k = 0; k < n_inst; ++k)
+      if (scene.instances[k].visible) iprims[n_vis++] = iprims[k];
+    iprims.resize(n_vis);
+  }
   lap("instance world boxes");
   std::vector<TreeNode> top;
   int top_depth = 0;
@@ -495,7 +503,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
       sig.push_back(mesh_nodes(mi).size());
     }
   sig.push_back(~0ull);
-  for (const Instance& in : scene.instances) sig.push_back(in.mesh);
+  for (const Instance& in : scene.instances) sig.push_back(((uint64_t)in.visible << 32) | in.mesh);
   BlobHeader old_hdr{};
   if (blob.size() >= sizeof old_hdr) std::memcpy(&old_hdr, blob.data(), sizeof old_hdr);
   const bool patch = n_inst && blob.size() == off && sig == scene.blob_signature && old_hdr.magic == kBlobMagic &&

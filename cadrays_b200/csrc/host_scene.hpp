@@ -25,6 +25,7 @@ struct Instance {
   uint32_t mesh;
   uint32_t material;
   float    xf[12];             // row-major 3x4 object -> world
+  bool     visible = true;     // hidden instances keep their id and records but are left out of the top-level tree
   // world box of the transformed vertices, kept with the transform and mesh it was computed for: a commit after
   // one object moved transforms the vertices of that object only
   mutable bool     box_valid = false;

@@ -284,6 +284,10 @@ class V3d_View:
     def SetMaterialIndex(self, inst_id: int, material_id: int):
         check(self._lib.crt_instance_set_material(self._ctx, int(inst_id), int(material_id)))
 
+    def SetVisible(self, inst_id: int, visible: bool):
+        """AIS Erase / Display of an object that stays in the scene (takes effect at the next Update())."""
+        check(self._lib.crt_instance_set_visible(self._ctx, int(inst_id), int(bool(visible))))
+
     def Clear(self):
         check(self._lib.crt_scene_clear(self._ctx))
 

@@ -183,6 +183,10 @@ int crt_instance_add(crt_context* ctx, uint32_t mesh_id, const float xf[12],
                      uint32_t material_id, uint32_t* out_inst_id);
 int crt_instance_set_transform(crt_context* ctx, uint32_t inst_id, const float xf[12]);
 int crt_instance_set_material(crt_context* ctx, uint32_t inst_id, uint32_t material_id);
+/* AIS_InteractiveContext::Erase / Display of an object that stays in the scene tree (the eye toggle of CADRays'
+ * scene panel; `verase` / `vdisplay` in scripts): a hidden instance keeps its id, transform and material but is left
+ * out of the top-level tree at the next crt_commit.  Bottom-level trees are untouched. */
+int crt_instance_set_visible(crt_context* ctx, uint32_t inst_id, int visible);
 /* vclear (data/scripts/CornellBox.tcl:8): drops meshes and instances. */
 int crt_scene_clear(crt_context* ctx);
 

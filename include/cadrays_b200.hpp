@@ -107,6 +107,7 @@ public:
   uint32_t Display(uint32_t mesh, const float trsf3x4[12], uint32_t material)
   { uint32_t id = 0; check(crt_instance_add(myCtx, mesh, trsf3x4, material, &id)); return id; }
   void SetLocation(uint32_t inst, const float trsf3x4[12]) { check(crt_instance_set_transform(myCtx, inst, trsf3x4)); }
+  void SetVisible(uint32_t inst, bool visible) { check(crt_instance_set_visible(myCtx, inst, visible)); }   // Erase / Display
   void Clear() { check(crt_scene_clear(myCtx)); }
   void SetMaterials(const std::vector<BSDF>& m)
   {

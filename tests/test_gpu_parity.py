@@ -617,3 +617,27 @@ def test_regression_harness_end_to_end(tmp_path, product_lib):
     report = open(os.path.join(second, "Result.html"), encoding="utf-8").read()
     assert "identical" in report and "pixels differ" not in report
     assert "Scene.tcl" in regress.read_rates(os.path.join(second, "Result.html"))
+
+
+def test_hidden_instance_parity(product_lib, oracle_lib):
+    """crt_instance_set_visible on the device path: hide an object, commit, render -- bit-equal to the oracle walking
+    the re-exported blob; show it again and the first image comes back."""
+    from oracle.oracle_ffi import OracleScene
+    desc = scenes.cornell_box(96, 96, depth=4, sphere_res=(24, 12))
+    view, orc = _pair(desc)
+    view.Redraw(3)
+    before = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft).copy()
+    view.SetVisible(5, False)                      # the glass sphere
+    view.Update()
+    view.Redraw(3)
+    hidden = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft).copy()
+    o2 = OracleScene(view.ExportBVH())
+    o2.configure(desc)
+    assert np.array_equal(hidden, o2.hdr(o2.render(96, 96, 3)))
+    assert not np.array_equal(hidden, before)
+    view.SetVisible(5, True)
+    view.Update()
+    view.Redraw(3)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), before)
+    o2.close()
+    view.Remove()

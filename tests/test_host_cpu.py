@@ -300,6 +300,43 @@ def test_blob_patch_shortcut_never_keeps_stale_geometry(product_lib):
     v.Remove()
 
 
+def test_hidden_instances_leave_the_top_level_tree(product_lib, oracle_lib):
+    """crt_instance_set_visible (AIS Erase / Display): a hidden instance keeps its id and records but no top-level
+    leaf refers to it, so the oracle renders exactly the scene without that object; showing it again restores the
+    original blob; hiding everything gives an empty scene."""
+    from oracle.oracle_ffi import OracleScene
+    desc = scenes.cornell_box(40, 40, depth=3, sphere_res=(12, 6))
+    v = V3d_View(host_only=True)
+    desc.apply(v, with_target=False)
+    original = v.ExportBVH()
+    hidden = 6                                           # the yellow box
+    v.SetVisible(hidden, False)
+    v.Update()
+    blob = v.ExportBVH()
+    h = _parse_blob(blob)
+    assert h["hdr"]["n_inst"] == len(desc.instances)
+    leaves = h["info"][:h["hdr"]["n_top"], 0]
+    assert hidden + 1 not in leaves and sorted(x for x in leaves if x > 0) == [k + 1 for k in range(len(desc.instances)) if k != hidden]
+    o = OracleScene(blob); o.configure(desc)
+    without = scenes.cornell_box(40, 40, depth=3, sphere_res=(12, 6))
+    del without.instances[hidden]
+    v2 = V3d_View(host_only=True)
+    without.apply(v2, with_target=False)
+    o2 = OracleScene(v2.ExportBVH()); o2.configure(without)
+    assert np.array_equal(o.render(40, 40, 3), o2.render(40, 40, 3))
+    o.close(); o2.close(); v2.Remove()
+    v.SetVisible(hidden, True)
+    v.Update()
+    assert v.ExportBVH() == original
+    for k in range(len(desc.instances)):
+        v.SetVisible(k, False)
+    v.Update()
+    assert _parse_blob(v.ExportBVH())["hdr"]["n_inst"] == 0
+    with pytest.raises(CrtError):
+        v.SetVisible(999, True)
+    v.Remove()
+
+
 def test_parallel_tree_build_is_deterministic(monkeypatch, product_lib):
     """Meshes of 200 k triangles and more are built on several threads (upper levels with parallel passes over the
     wide nodes, sub-trees as independent tasks, then renumbered): the blob is byte-identical to the single-thread
