@@ -1,5 +1,4 @@
 """Small adaptive-sampling + pipelined render for compute-sanitizer runs (memcheck / racecheck / initcheck)."""
-import os
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
