@@ -785,13 +785,20 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
   out.tri_verts.assign(kTriStride * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
   out.tri_nrm.assign(3 * (size_t)h.n_tris, f4{ 0, 0, 0, 0 });
   out.tri_uv.assign(6 * (size_t)h.n_tris, 0.0f);
-  for (size_t t = 0; t < h.n_tris; ++t) {
+  bool bad_index = false;
+#pragma omp parallel for schedule(static) if (h.n_tris >= 100000)
+  for (long tt = 0; tt < (long)h.n_tris; ++tt) {
+    const size_t t = (size_t)tt;
     const int32_t* tr = v.tris + 4 * t;
     const int32_t vo = tri_voff[t];
     if (vo < 0) continue;   // triangle of an unreferenced range
     for (int k = 0; k < 3; ++k) {
       const int64_t vi = (int64_t)vo + tr[k];
-      if (vi < 0 || vi >= (int64_t)h.n_verts) { err = "blob: vertex index"; return false; }
+      if (vi < 0 || vi >= (int64_t)h.n_verts) {
+#pragma omp atomic write
+        bad_index = true;
+        break;
+      }
       const float* p = v.vert_pos + 3 * (size_t)vi;
       const float* n = v.vert_nrm + 3 * (size_t)vi;
       out.tri_verts[kTriStride * t + k] = f4{ p[0], p[1], p[2], 0.0f };
@@ -801,6 +808,7 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
     }
     out.tri_verts[kTriStride * t].w = Converter::bits(tr[3]);
   }
+  if (bad_index) { err = "blob: vertex index"; return false; }
   out.inst.assign(4 * (size_t)h.n_inst, f4{ 0, 0, 0, 0 });
   for (size_t k = 0; k < h.n_inst; ++k) {
     const float* m = v.inst_inv + 16 * k;
