@@ -440,3 +440,32 @@ foreach {n x m} {s1 0 gold s2 1 jade s3 2 glass} { ball $n $x 0 0 $m }
 """)
     d = s.scene()
     assert len(d.instances) == 3 and [round(float(xf[0, 3])) for _, xf, _ in d.instances] == [0, 1, 2]
+
+
+def test_ply_round_trip_randomised(tmp_path):
+    """write_ply / read_ply over random meshes (hypothesis): binary and ASCII, with and without normals and texel
+    coordinates; binary files reproduce the floats bit for bit, ASCII ones to print precision."""
+    from hypothesis import given, settings, strategies as st
+    from cadrays_b200 import ply
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(nv=st.integers(3, 40), nt=st.integers(1, 60), binary=st.booleans(), with_n=st.booleans(), with_uv=st.booleans(),
+           seed=st.integers(0, 2**31))
+    def check(nv, nt, binary, with_n, with_uv, seed):
+        g = np.random.default_rng(seed)
+        pos = (g.normal(size=(nv, 3)) * 10.0 ** int(g.integers(-3, 4))).astype(np.float32)
+        nrm = g.normal(size=(nv, 3)).astype(np.float32) if with_n else None
+        uv = g.random((nv, 2)).astype(np.float32) if with_uv else None
+        idx = g.integers(0, nv, size=(nt, 3)).astype(np.uint32)
+        counter[0] += 1
+        path = str(tmp_path / f"m{counter[0]}.ply")
+        ply.write_ply(path, pos, nrm, idx, binary=binary, uv=uv)
+        p2, n2, uv2, i2 = ply.read_ply(path)
+        assert np.array_equal(i2, idx) and p2.shape == pos.shape
+        same = np.array_equal if binary else (lambda a, b: np.allclose(a, b, rtol=1e-6, atol=1e-30))
+        assert same(p2, pos)
+        assert (n2 is None) == (nrm is None) and (nrm is None or same(n2, nrm))
+        assert (uv2 is None) == (uv is None) and (uv is None or same(uv2, uv))
+
+    check()
