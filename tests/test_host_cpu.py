@@ -2,6 +2,7 @@
 exports every symbol include/cadrays_b200.h declares, the host BVH builder produces a well-formed
 two-level tree, the host mirror keeps CADRays' material semantics, and device entry points fail
 loudly without a device."""
+import os
 import re
 import struct
 from pathlib import Path
@@ -363,6 +364,21 @@ def test_parallel_tree_build_is_deterministic(monkeypatch, product_lib):
     monkeypatch.delenv("CRT_BUILD_SERIAL")
     monkeypatch.setenv("OMP_NUM_THREADS", "3")      # read by libgomp at load time only; the std::thread passes still vary
     assert blob() == serial
+
+
+def test_host_scene_under_sanitizers(tmp_path):
+    """cadrays_b200/csrc/host_scene.cpp built with AddressSanitizer + UBSan and driven by tests/cpp/host_scene_sanitize.cpp:
+    random scenes through build -> parse -> device layout for both tree widths, edit sequences (patched blob = fresh
+    build), bit-flipped and truncated blobs, singular transforms."""
+    import subprocess
+    exe = tmp_path / "host_scene_sanitize"
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fopenmp", "-Wall",
+           str(REPO / "tests" / "cpp" / "host_scene_sanitize.cpp"), str(REPO / "cadrays_b200" / "csrc" / "host_scene.cpp"), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "host scene sanitize ok" in r.stdout, (r.returncode, r.stdout[-2000:], r.stderr[-4000:])
 
 
 def test_recommit_after_edit_equals_fresh_build(product_lib):
