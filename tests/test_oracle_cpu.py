@@ -543,3 +543,23 @@ def test_adaptive_allocation_randomised(oracle_lib):
         assert (np.diff(ks) >= -1).all()      # systematic sampling: monotone in the weight up to one sample
 
     check()
+
+
+def test_oracle_under_sanitizers(tmp_path):
+    """oracle/cadrays_oracle.c built with AddressSanitizer + UBSan (tests/cpp/oracle_sanitize.cpp): every material
+    class, both light kinds, environment, textures, thin lens, both tree widths, degenerate rays; traces, brute
+    force, plain and adaptive renders, display."""
+    import os
+    import subprocess
+    repo = Path(__file__).resolve().parent.parent
+    obj, exe = tmp_path / "oracle.o", tmp_path / "oracle_sanitize"
+    san = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fopenmp"]
+    r = subprocess.run(["gcc", *san, "-mfma", "-ffp-contract=off", "-c", str(repo / "oracle" / "cadrays_oracle.c"), "-o", str(obj)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", *san, "-Wall", str(repo / "tests" / "cpp" / "oracle_sanitize.cpp"),
+                        str(repo / "cadrays_b200" / "csrc" / "host_scene.cpp"), str(obj), "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and "oracle sanitize ok" in r.stdout, (r.returncode, r.stdout[-2000:], r.stderr[-4000:])
+
