@@ -397,6 +397,17 @@ class V3d_View:
         check(self._lib.crt_adaptive_tiles_get(self._ctx, counts.ctypes.data_as(u32), errs.ctypes.data_as(u32), n, None, None))
         return counts.reshape(ty.value, tx.value), errs.reshape(ty.value, tx.value)
 
+    def ToPixMap(self, width: int, height: int, buffer_type: int = Graphic3d_BT_RGB, samples: Optional[int] = None) -> np.ndarray:
+        """V3d_View::ToPixMap(Image_PixMap&, width, height, bufferType): an off-screen render at the given size --
+        resize, render `samples` (default SamplesPerPixel) samples per pixel, dump.  CADRays itself uses BufferDump on
+        the live view (AppViewer.cxx:1259-1262); ToPixMap is what DRAW's `vdump -width -height` goes through."""
+        self.SetWindowSize(int(width), int(height))
+        cam = self._camera
+        cam.Aspect = float(width) / float(height)
+        self.SetCamera(cam)
+        self.Redraw(samples)
+        return self.BufferDump(buffer_type)
+
     def AccumDevicePtr(self):
         p = C.c_void_p()
         n = C.c_size_t()

@@ -127,6 +127,17 @@ public:
   // BufferDump(Image_PixMap&, Graphic3d_BT_RGB) returns bool in OCCT (AppGui.cxx:430-433)
   bool BufferDump(std::vector<uint8_t>& rgb8) { rgb8.resize((size_t)myW * myH * 3); return crt_read_ldr(myCtx, rgb8.data(), 0) == CRT_OK; }
   bool BufferDumpHdr(std::vector<float>& rgb) { rgb.resize((size_t)myW * myH * 3); return crt_read_hdr(myCtx, rgb.data(), 0) == CRT_OK; }
+  // V3d_View::ToPixMap(Image_PixMap&, width, height): off-screen render at the given size (the camera passed in keeps
+  // its pose; its aspect is set from the size), `samples` samples per pixel, RGB8 dump.  Returns false like OCCT.
+  bool ToPixMap(std::vector<uint8_t>& rgb8, uint32_t w, uint32_t h, crt_camera cam, uint32_t samples)
+  {
+    SetWindowSize(w, h);
+    cam.aspect = (float)w / (float)h;
+    SetCamera(cam);
+    uint64_t n = 0;
+    if (crt_render(myCtx, samples, &n) != CRT_OK) return false;
+    return BufferDump(rgb8);
+  }
   std::vector<uint8_t> ExportBVH()
   {
     size_t n = 0; check(crt_bvh_export(myCtx, nullptr, 0, &n));

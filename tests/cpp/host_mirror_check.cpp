@@ -29,6 +29,13 @@ int main()
   std::printf("blob %zu bytes\n", blob.size());
   try { view.Redraw(); return 4; }                    // no device bound: must fail loudly
   catch (const crt::Failure& f) { if (f.code != CRT_ERR_STATE && f.code != CRT_ERR_NO_DEVICE) return 5; }
+  {
+    std::vector<uint8_t> px;
+    crt_camera cam = {};
+    cam.dir[1] = 1.f; cam.up[2] = 1.f; cam.fovy_deg = 45.f;
+    try { if (view.ToPixMap(px, 32, 16, cam, 1)) return 9; }      // host-only: resize refuses, nothing is rendered
+    catch (const crt::Failure& f) { if (f.code != CRT_ERR_NO_DEVICE && f.code != CRT_ERR_STATE) return 10; }
+  }
   try { view.Display(99, nullptr, 0); return 6; }
   catch (const crt::Failure& f) { if (f.code != CRT_ERR_INVALID_ARG) return 7; }
   return blob.size() > 64 ? 0 : 8;

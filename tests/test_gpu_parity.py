@@ -641,3 +641,19 @@ def test_hidden_instance_parity(product_lib, oracle_lib):
     assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft), before)
     o2.close()
     view.Remove()
+
+
+def test_to_pix_map_off_screen_size(product_lib, oracle_lib):
+    """V3d_View::ToPixMap (named in the north star next to Redraw): an off-screen render at another size equals the
+    oracle at that size and aspect; the accumulation restarts because the target changed."""
+    desc = scenes.cornell_box(64, 64, depth=4, sphere_res=(16, 8))
+    view, orc = _pair(desc)
+    view.Redraw(2)
+    img = view.ToPixMap(120, 72, Graphic3d_BT_RGB_RayTraceHdrLeft, samples=3)
+    assert img.shape == (72, 120, 3)
+    desc.width, desc.height = 120, 72
+    orc.configure(desc)                   # camera aspect follows the new size
+    assert np.array_equal(img, orc.hdr(orc.render(120, 72, 3)))
+    ldr = view.ToPixMap(64, 64, samples=1)
+    assert ldr.shape == (64, 64, 3) and ldr.dtype == np.uint8
+    view.Remove()
