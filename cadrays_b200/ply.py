@@ -36,8 +36,9 @@ def read_ply(path: str) -> Tuple[np.ndarray, Optional[np.ndarray], Optional[np.n
                 elements[-1][2].append(("list", t[4], t[2], t[3]))
             else:
                 elements[-1][2].append(("scalar", t[2], t[1]))
-    if fmt not in ("ascii", "binary_little_endian"):
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
         raise ValueError(f"unsupported PLY format {fmt}")
+    E = ">" if fmt == "binary_big_endian" else "<"
     verts = None
     faces = []
     if fmt == "ascii":
@@ -63,23 +64,34 @@ def read_ply(path: str) -> Tuple[np.ndarray, Optional[np.ndarray], Optional[np.n
     else:
         off = end
         vcols, face_lists = {}, []
+        fast_tris = None
         for name, count, props in elements:
             if all(p[0] == "scalar" for p in props):
-                dt = np.dtype([(p[1], "<" + _TYPES[p[2]]) for p in props])
+                dt = np.dtype([(p[1], E + _TYPES[p[2]]) for p in props])
                 arr = np.frombuffer(data, dtype=dt, count=count, offset=off)
                 off += dt.itemsize * count
                 if name == "vertex":
                     vcols = {n: arr[n].astype(np.float64) for n in arr.dtype.names}
             else:
+                # fast path: one list property and every face a triangle (what exporters write): fixed-size records
+                if name == "face" and len(props) == 1 and count > 0:
+                    cdt, idt = np.dtype(E + _TYPES[props[0][2]]), np.dtype(E + _TYPES[props[0][3]])
+                    rec = np.dtype([("n", cdt), ("i", idt, (3,))])
+                    if off + rec.itemsize * count <= len(data):
+                        arr = np.frombuffer(data, dtype=rec, count=count, offset=off)
+                        if (arr["n"] == 3).all():
+                            fast_tris = arr["i"].astype(np.int64)
+                            off += rec.itemsize * count
+                            continue
                 for _ in range(count):
                     row_list = None
                     for p in props:
                         if p[0] == "scalar":
-                            off += struct.calcsize("<" + _TYPES[p[2]])
+                            off += struct.calcsize(E + _TYPES[p[2]])
                         else:
-                            (n,) = struct.unpack_from("<" + _TYPES[p[2]], data, off)
-                            off += struct.calcsize("<" + _TYPES[p[2]])
-                            f = "<" + str(n) + _TYPES[p[3]]
+                            (n,) = struct.unpack_from(E + _TYPES[p[2]], data, off)
+                            off += struct.calcsize(E + _TYPES[p[2]])
+                            f = E + str(n) + _TYPES[p[3]]
                             row_list = list(struct.unpack_from(f, data, off))
                             off += struct.calcsize(f)
                     if name == "face" and row_list is not None:
@@ -97,7 +109,12 @@ def read_ply(path: str) -> Tuple[np.ndarray, Optional[np.ndarray], Optional[np.n
     for f in face_lists:
         for k in range(1, len(f) - 1):
             tris.append((f[0], f[k], f[k + 1]))
-    idx = np.array(tris, dtype=np.uint32).reshape(-1, 3)
+    idx = np.array(tris, dtype=np.int64).reshape(-1, 3)
+    if fmt != "ascii" and fast_tris is not None:
+        idx = fast_tris if idx.size == 0 else np.concatenate([fast_tris, idx])
+    if idx.size and idx.min() < 0:
+        raise ValueError("PLY face index out of range")
+    idx = idx.astype(np.uint32)
     if idx.size and idx.max() >= pos.shape[0]:
         raise ValueError("PLY face index out of range")
     return pos, nrm, uv, idx
@@ -120,8 +137,10 @@ def write_ply(path: str, pos, nrm, idx, binary: bool = True, uv=None) -> None:
             v = np.hstack([v, np.asarray(uv, np.float32)])
         if binary:
             f.write(v.astype("<f4").tobytes())
-            for t in idx:
-                f.write(struct.pack("<B3I", 3, *[int(x) for x in t]))
+            rec = np.zeros(idx.shape[0], dtype=np.dtype([("n", "u1"), ("i", "<u4", (3,))]))
+            rec["n"] = 3
+            rec["i"] = idx
+            f.write(rec.tobytes())
         else:
             for r in v:
                 f.write((" ".join(repr(float(x)) for x in r) + "\n").encode())

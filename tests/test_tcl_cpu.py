@@ -469,3 +469,30 @@ def test_ply_round_trip_randomised(tmp_path):
         assert (uv2 is None) == (uv is None) and (uv is None or same(uv2, uv))
 
     check()
+
+
+def test_ply_big_endian_polygons_and_large_meshes(tmp_path):
+    """read_ply beyond what write_ply produces: big-endian binary, uchar / int list types, a quad next to a triangle
+    (fan triangulation); and the vectorised path for all-triangle files (a 100 k-face mesh in well under a second)."""
+    import struct
+    import time
+    from cadrays_b200 import ply
+    hdr = (b"ply\nformat binary_big_endian 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+           b"element face 2\nproperty list uchar int vertex_indices\nend_header\n")
+    body = struct.pack(">12f", 0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0) + struct.pack(">B4i", 4, 0, 1, 2, 3) + struct.pack(">B3i", 3, 0, 2, 3)
+    (tmp_path / "be.ply").write_bytes(hdr + body)
+    p, n, uv, i = ply.read_ply(str(tmp_path / "be.ply"))
+    assert p.tolist() == [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]] and n is None and uv is None
+    assert i.tolist() == [[0, 1, 2], [0, 2, 3], [0, 2, 3]]
+    pos, nrm, idx = scenes.uv_sphere(1.0, 330, 165)
+    assert idx.shape[0] > 100_000
+    t0 = time.perf_counter()
+    ply.write_ply(str(tmp_path / "big.ply"), pos, nrm, idx, binary=True)
+    p2, n2, _, i2 = ply.read_ply(str(tmp_path / "big.ply"))
+    assert time.perf_counter() - t0 < 2.0
+    assert np.array_equal(p2, pos) and np.array_equal(n2, nrm) and np.array_equal(i2, idx)
+    bad = bytearray((tmp_path / "be.ply").read_bytes())
+    bad[-1] = 9                                   # index 9 of 4 vertices
+    (tmp_path / "bad.ply").write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        ply.read_ply(str(tmp_path / "bad.ply"))
