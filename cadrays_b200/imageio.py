@@ -108,3 +108,59 @@ def write_pfm(path: str, rgb32f_bottom_up: np.ndarray) -> None:
     with open(path, "wb") as f:
         f.write(f"PF\n{w} {h}\n-1.0\n".encode())
         f.write(img.tobytes())
+
+
+def read_hdr(path: str) -> np.ndarray:
+    """Radiance RGBE (.hdr / .pic), flat or new-style run-length encoded scanlines, -Y +X orientation.
+    Returns float32 RGB, top-down rows (what vtextureenv hands to crt_envmap_set_rgb32f)."""
+    data = open(path, "rb").read()
+    if not data.startswith(b"#?"):
+        raise ValueError(f"{path}: not a Radiance picture")
+    end = data.index(b"\n\n") + 2
+    line_end = data.index(b"\n", end)
+    res = data[end:line_end].split()
+    if len(res) != 4 or res[0] != b"-Y" or res[2] != b"+X":
+        raise ValueError(f"{path}: unsupported orientation {data[end:line_end]!r}")
+    h, w = int(res[1]), int(res[3])
+    pos = line_end + 1
+    rgbe = np.zeros((h, w, 4), dtype=np.uint8)
+    for y in range(h):
+        if 8 <= w < 32768 and data[pos] == 2 and data[pos + 1] == 2 and not (data[pos + 2] & 0x80):
+            if (data[pos + 2] << 8 | data[pos + 3]) != w:
+                raise ValueError(f"{path}: scanline width mismatch")
+            pos += 4
+            for c in range(4):
+                x = 0
+                while x < w:
+                    n = data[pos]; pos += 1
+                    if n > 128:
+                        n -= 128
+                        rgbe[y, x:x + n, c] = data[pos]; pos += 1
+                    else:
+                        rgbe[y, x:x + n, c] = np.frombuffer(data, np.uint8, n, pos); pos += n
+                    x += n
+                if x != w:
+                    raise ValueError(f"{path}: corrupt run-length data")
+        else:
+            rgbe[y] = np.frombuffer(data, np.uint8, 4 * w, pos).reshape(w, 4); pos += 4 * w
+    e = rgbe[..., 3].astype(np.int32)
+    scale = np.where(e > 0, np.ldexp(1.0, e - 136), 0.0).astype(np.float32)
+    return (rgbe[..., :3].astype(np.float32) * scale[..., None]).astype(np.float32)
+
+
+def read_pfm(path: str) -> np.ndarray:
+    """Portable float map (PF colour / Pf grey), either byte order; returns float32 RGB, top-down rows."""
+    with open(path, "rb") as f:
+        kind = f.readline().strip()
+        dims = f.readline().split()
+        while len(dims) < 2:
+            dims += f.readline().split()
+        w, h = int(dims[0]), int(dims[1])
+        scale = float(f.readline().strip())
+        ch = {b"PF": 3, b"Pf": 1}.get(kind)
+        if ch is None:
+            raise ValueError(f"{path}: not a PFM file")
+        a = np.frombuffer(f.read(4 * w * h * ch), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, ch)
+    img = a[::-1].astype(np.float32)          # PFM rows are bottom-up
+    return np.repeat(img, 3, axis=2) if ch == 1 else img
+

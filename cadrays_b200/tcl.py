@@ -1095,8 +1095,19 @@ class DrawSession(Interp):
             self.output.append(f"vtextureenv: cannot read '{path}', no environment map")
             self.envmap = None
             return
-        from PIL import Image
-        self.envmap = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+        ext = os.path.splitext(path)[1].lower()
+        if ext in (".hdr", ".pic"):              # floating-point maps keep their range (crt_envmap_set_rgb32f)
+            from .imageio import read_hdr
+            self.envmap = read_hdr(path)
+        elif ext == ".pfm":
+            from .imageio import read_pfm
+            self.envmap = read_pfm(path)
+        elif ext == ".png":
+            from .imageio import read_png_rgb8
+            self.envmap = read_png_rgb8(path)
+        else:
+            from PIL import Image
+            self.envmap = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
 
     def _d_vfps(self, a):
         if a and self._is_num(a[0]):

@@ -496,3 +496,53 @@ def test_ply_big_endian_polygons_and_large_meshes(tmp_path):
     (tmp_path / "bad.ply").write_bytes(bytes(bad))
     with pytest.raises(ValueError):
         ply.read_ply(str(tmp_path / "bad.ply"))
+
+
+def test_float_environment_maps(tmp_path):
+    """`vtextureenv on file.hdr|.pfm`: Radiance RGBE (flat and new-style run-length scanlines) and PFM (both byte
+    orders, colour and grey) load as float radiance, top-down rows; 8-bit formats stay 8-bit (they are linearised
+    by crt_envmap_set_rgb8)."""
+    g = np.random.default_rng(2)
+    img = (g.random((9, 40, 3)) ** 3 * 20).astype(np.float32)
+    imageio.write_hdr(str(tmp_path / "flat.hdr"), img[::-1])
+    back = imageio.read_hdr(str(tmp_path / "flat.hdr"))
+    assert back.shape == img.shape and back.dtype == np.float32
+    assert (np.abs(back - img) <= img.max(axis=2, keepdims=True) / 128 + 1e-7).all()      # 8-bit mantissa, truncated
+    # the same pixels, run-length encoded by hand: per scanline 02 02 hi lo, then four channel planes of runs / literals
+    raw = open(tmp_path / "flat.hdr", "rb").read()
+    head_end = raw.index(b"\n", raw.index(b"\n\n") + 2) + 1
+    rgbe = np.frombuffer(raw, np.uint8, offset=head_end).reshape(9, 40, 4)
+    out = bytearray(raw[:head_end])
+    for y in range(9):
+        out += bytes([2, 2, 0, 40])
+        for c in range(4):
+            row = rgbe[y, :, c]
+            x = 0
+            while x < 40:
+                run = 1
+                while x + run < 40 and run < 127 and row[x + run] == row[x]:
+                    run += 1
+                if run >= 3:
+                    out += bytes([128 + run, int(row[x])]); x += run
+                else:
+                    lit = min(40 - x, 5)
+                    out += bytes([lit]) + row[x:x + lit].tobytes(); x += lit
+    (tmp_path / "rle.hdr").write_bytes(bytes(out))
+    assert np.array_equal(imageio.read_hdr(str(tmp_path / "rle.hdr")), back)
+    imageio.write_pfm(str(tmp_path / "le.pfm"), img[::-1])
+    assert np.array_equal(imageio.read_pfm(str(tmp_path / "le.pfm")), img)
+    with open(tmp_path / "be_grey.pfm", "wb") as f:
+        f.write(b"Pf\n40 9\n1.0\n" + img[::-1, :, 0].astype(">f4").tobytes())
+    grey = imageio.read_pfm(str(tmp_path / "be_grey.pfm"))
+    assert grey.shape == (9, 40, 3) and np.array_equal(grey[..., 1], img[..., 0])
+    s = tcl.DrawSession(32, 32)
+    s.eval(f"vtextureenv on {tmp_path / 'rle.hdr'}")
+    assert s.envmap.dtype == np.float32 and np.array_equal(s.envmap, back)
+    s.eval(f"vtextureenv on {tmp_path / 'le.pfm'}")
+    assert np.array_equal(s.envmap, img)
+    imageio.write_png(str(tmp_path / "ldr.png"), (np.clip(img, 0, 1) * 255).astype(np.uint8)[::-1])
+    s.eval(f"vtextureenv on {tmp_path / 'ldr.png'}")
+    assert s.envmap.dtype == np.uint8 and s.envmap.shape == (9, 40, 3)
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.hdr").write_bytes(b"P6 nope")
+        imageio.read_hdr(str(tmp_path / "bad.hdr"))
