@@ -546,3 +546,29 @@ def test_float_environment_maps(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "bad.hdr").write_bytes(b"P6 nope")
         imageio.read_hdr(str(tmp_path / "bad.hdr"))
+
+
+def test_tcl_expr_arithmetic_randomised():
+    """tcl_expr on random arithmetic (hypothesis): integer expressions follow Tcl (floor division and modulo like
+    Python's, C operator spellings), mixed expressions follow IEEE doubles; comparisons and logic give 0 / 1."""
+    from hypothesis import given, settings, strategies as st
+
+    ints = st.integers(-50, 50)
+
+    @settings(max_examples=200, deadline=None)
+    @given(a=ints, b=ints, c=st.integers(1, 20), x=st.floats(-100, 100, allow_nan=False))
+    def check(a, b, c, x):
+        assert tcl.tcl_expr(f"{a} + {b} * {c}") == a + b * c
+        assert tcl.tcl_expr(f"({a} - {b}) / {c}") == (a - b) // c
+        assert tcl.tcl_expr(f"{a} % {c}") == a % c
+        assert tcl.tcl_expr(f"{a} < {b} || {a} >= {b}") == 1
+        assert tcl.tcl_expr(f"{a} == {b} && {a} != {b}") == 0
+        assert tcl.tcl_expr(f"!({a} > {b})") == int(not a > b)
+        assert tcl.tcl_expr(f"{x!r} * 2.0 + {a}") == x * 2.0 + a
+        assert tcl.tcl_expr(f"abs({a}) + max({b}, {c})") == abs(a) + max(b, c)
+
+    check()
+    assert tcl.tcl_expr("7 / 2") == 3 and tcl.tcl_expr("-7 / 2") == -4 and tcl.tcl_expr("7 / 2.0") == 3.5
+    assert tcl.tcl_expr("1 << 4 | 3") == 19 and tcl.tcl_expr("sqrt(16) + pow(2, 3)") == 12.0
+    with pytest.raises(tcl.TclError):
+        tcl.tcl_expr("1 +")
