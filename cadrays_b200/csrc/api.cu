@@ -96,6 +96,7 @@ struct crt_context {
   DevBuf<uint32_t> d_tex_table;
   DeviceScene ds{};
   DeviceParams dp{};
+  size_t arena_nodes = 0, arena_inst_off = 0;   // float4 offsets of the sections inside d_arena (partial re-upload)
 
   // path state
   DevBuf<float4> ray_o, ray_d, thr, rad, hit, sh_o, sh_d, sh_c;
@@ -272,41 +273,66 @@ uint32_t auto_batch(const crt_context* c)
 
 int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
 {
+  // validate before anything on the device changes: a failed upload must leave the previous layout usable
+  if (L.quad ? 3 * (L.max_depth_top + L.max_depth_bottom) + 4 > kStackSizeQuad : L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
+    return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
   // one arena [nodes | triangle vertices | instances | vertex normals]: the traversal working set is
   // contiguous, so a single L2 access-policy window can cover it
   auto pad = [](size_t n) { return (n + 15u) & ~(size_t)15u; };   // float4 units, 256-byte sections
   const size_t n_nodes = pad(std::max<size_t>(L.nodes.size(), 4)), n_verts = pad(std::max<size_t>(L.tri_verts.size(), 3));
   const size_t n_inst = pad(std::max<size_t>(L.inst.size(), 4)), n_nrm = pad(std::max<size_t>(L.tri_nrm.size(), 3));
-  CRT_CUDA(c->d_arena.ensure(n_nodes + n_verts + n_inst + n_nrm));
+  // new buffers are allocated before the old ones are released (DevBuf::ensure frees first, so grow into
+  // temporaries and swap): an out-of-memory failure keeps c->ds pointing at live memory
+  const size_t n_arena = n_nodes + n_verts + n_inst + n_nrm, n_uv = std::max<size_t>(L.tri_uv.size() / 2, 3);
+  const uint32_t n_cache = L.quad ? 0u : std::min<uint32_t>(L.n_top_inner, 1024u);
+  const size_t n_cache4 = (size_t)5 * std::max<uint32_t>(n_cache, 1);
+  DevBuf<float4> arena_new, cache_new;
+  DevBuf<float2> uv_new;
+  const bool grow_arena = n_arena > c->d_arena.n || !c->d_arena.p, grow_uv = n_uv > c->d_tri_uv.n || !c->d_tri_uv.p;
+  const bool grow_cache = n_cache4 > c->d_top_cache.n || !c->d_top_cache.p;
+  cudaError_t ae = cudaSuccess;
+  if (grow_arena) ae = arena_new.ensure(n_arena);
+  if (ae == cudaSuccess && grow_uv) ae = uv_new.ensure(n_uv);
+  if (ae == cudaSuccess && grow_cache) ae = cache_new.ensure(n_cache4);
+  if (ae != cudaSuccess) {
+    arena_new.release(); uv_new.release(); cache_new.release();
+    cudaGetLastError();
+    return fail(ae == cudaErrorMemoryAllocation ? CRT_ERR_OUT_OF_MEMORY : CRT_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(ae));
+  }
+  // from here on the previous layout is being replaced: a failure leaves the context without one
+  c->has_layout = false;
+  CRT_CUDA(cudaStreamSynchronize(c->stream));       // no kernel still reads the buffers about to be released
+  if (grow_arena) { c->d_arena.release(); c->d_arena = arena_new; }
+  if (grow_uv) { c->d_tri_uv.release(); c->d_tri_uv = uv_new; }
+  if (grow_cache) { c->d_top_cache.release(); c->d_top_cache = cache_new; }
   float4* nodes = c->d_arena.p;
   float4* verts = nodes + n_nodes;
   float4* inst = verts + n_verts;
   float4* nrm = inst + n_inst;
+  c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
+  c->ds.tri_uv = c->d_tri_uv.p;
+  c->ds.top_cache = c->d_top_cache.p;
+  c->ds.n_top_cache = 0;
+  c->ds.top_root = kRefNone;
+  c->arena_nodes = n_nodes; c->arena_inst_off = n_nodes + n_verts;
   if (!L.nodes.empty()) CRT_CUDA(cudaMemcpyAsync(nodes, L.nodes.data(), L.nodes.size() * 16, cudaMemcpyHostToDevice, c->stream));
   if (!L.tri_verts.empty()) CRT_CUDA(cudaMemcpyAsync(verts, L.tri_verts.data(), L.tri_verts.size() * 16, cudaMemcpyHostToDevice, c->stream));
   if (!L.tri_nrm.empty()) CRT_CUDA(cudaMemcpyAsync(nrm, L.tri_nrm.data(), L.tri_nrm.size() * 16, cudaMemcpyHostToDevice, c->stream));
   if (!L.inst.empty()) CRT_CUDA(cudaMemcpyAsync(inst, L.inst.data(), L.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
-  CRT_CUDA(c->d_tri_uv.ensure(std::max<size_t>(L.tri_uv.size() / 2, 3)));
   if (!L.tri_uv.empty()) CRT_CUDA(cudaMemcpyAsync(c->d_tri_uv.p, L.tri_uv.data(), L.tri_uv.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CRT_CUDA(cudaStreamSynchronize(c->stream));
-  c->ds.tri_uv = c->d_tri_uv.p;
   {
     // padded copy of the first top-level nodes (breadth-first = top of the tree) for shared-memory staging
-    const uint32_t n_cache = L.quad ? 0u : std::min<uint32_t>(L.n_top_inner, 1024u);
-    std::vector<f4> cache((size_t)5 * std::max<uint32_t>(n_cache, 1), f4{ 0, 0, 0, 0 });
+    std::vector<f4> cache(n_cache4, f4{ 0, 0, 0, 0 });
     for (uint32_t k = 0; k < n_cache; ++k)
       for (int q = 0; q < 4; ++q) cache[5 * (size_t)k + q] = L.nodes[4 * (size_t)k + q];
-    CRT_CUDA(c->d_top_cache.ensure(cache.size()));
-    CRT_CUDA(cudaMemcpy(c->d_top_cache.p, cache.data(), cache.size() * 16, cudaMemcpyHostToDevice));
-    c->ds.top_cache = c->d_top_cache.p;
+    CRT_CUDA(cudaMemcpyAsync(c->d_top_cache.p, cache.data(), cache.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
     c->ds.n_top_cache = n_cache;
   }
-  c->ds.nodes = nodes; c->ds.tri_verts = verts; c->ds.tri_nrm = nrm; c->ds.inst = inst;
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
   c->quad = L.quad;
-  if (L.quad ? 3 * (L.max_depth_top + L.max_depth_bottom) + 4 > kStackSizeQuad : L.max_depth_top + L.max_depth_bottom + 4 > kStackSize)
-    return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
   if (c->l2_persist) {
     // keep nodes + triangle vertices + instance records resident in the 126 MB L2 while gigabytes of
     // path state stream past them (hit ratio scaled to the set-aside the device allows)
@@ -781,7 +807,9 @@ int crt_instance_set_transform(crt_context* c, uint32_t inst, const float xf[12]
 {
   CRT_REQUIRE(c, "null context");
   CRT_REQUIRE(inst < c->scene.instances.size(), "unknown instance id");
-  std::memcpy(c->scene.instances[inst].xf, xf ? xf : k_identity, sizeof(float) * 12);
+  const float* src = xf ? xf : k_identity;
+  for (int k = 0; k < 12; ++k) if (!std::isfinite(src[k])) return fail(CRT_ERR_INVALID_ARG, "non-finite transform");
+  std::memcpy(c->scene.instances[inst].xf, src, sizeof(float) * 12);
   c->geometry_dirty = true;
   return CRT_OK;
 }
@@ -1203,7 +1231,12 @@ int crt_bvh_import(crt_context* c, const void* buf, size_t size)
   c->blob.swap(keep);
   c->scene.blob_signature.clear();      // the blob no longer comes from this context's scene
   rc = load_blob(c);
-  if (rc) { c->blob.swap(keep); return rc; }
+  if (rc) {
+    c->blob.swap(keep);
+    // the device may have lost its layout half way (upload_layout clears has_layout): the next crt_commit rebuilds it
+    if (!c->has_layout) c->geometry_dirty = true;
+    return rc;
+  }
   c->geometry_dirty = false;
   reset_accum_state(c);
   return CRT_OK;

@@ -424,11 +424,22 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   // object space with a differently rounded transform.  Visiting order only; hits are unaffected.
   std::vector<Prim> iprims(n_inst);
   std::vector<float> inv(16 * n_inst);
-  bool bad_xf = false;
+  int bad_xf = 0;
 #pragma omp parallel for schedule(dynamic, 8)
   for (long k = 0; k < (long)n_inst; ++k) {
     const Instance& in = scene.instances[k];
-    if (!invert_affine(in.xf, &inv[16 * k])) { bad_xf = true; continue; }
+    if (!in.visible) {
+      // not displayed: never entered by a ray, so its transform is neither inverted nor checked (identity record)
+      float* q = &inv[16 * k];
+      for (int e = 0; e < 16; ++e) q[e] = (e % 5 == 0) ? 1.0f : 0.0f;
+      iprims[k].id = (uint32_t)k;
+      continue;
+    }
+    if (!invert_affine(in.xf, &inv[16 * k])) {
+#pragma omp atomic write
+      bad_xf = 1;
+      continue;
+    }
     const Mesh& m = scene.meshes[in.mesh];
     Box b;
     if (in.box_valid && in.box_mesh == in.mesh && std::memcmp(in.box_xf, in.xf, sizeof in.xf) == 0) {
@@ -532,6 +543,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
     std::memcpy(nmin + 3 * n, t.lo, 12);
     std::memcpy(nmax + 3 * n, t.hi, 12);
     if (t.leaf) {
+      if (t.a != t.b) { err = "top-level leaf holds more than one instance (tree deeper than the builder's limit)"; return false; }
       const uint32_t k = iprims[t.a].id;   // leaf size 1
       const MeshTree& mt = trees[scene.instances[k].mesh];
       info[4 * n + 0] = (int32_t)k + 1;

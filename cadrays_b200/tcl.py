@@ -1162,6 +1162,7 @@ class DrawSession(Interp):
         s.envmap = self.envmap
         s.textures = list(self.textures)
         proj = self.proj / np.linalg.norm(self.proj)
+        auto_size = None
         if self.eye is not None and self.at is not None:
             eye, at = self.eye, self.at
         else:
@@ -1178,9 +1179,9 @@ class DrawSession(Interp):
                 dist = radius / math.sin(half_min)
             eye = at + proj * dist
             if self.size is None:
-                self.size = 2.0 * radius
+                auto_size = 2.0 * radius   # per call: a later vdump of a changed scene fits the scene as it is then
         s.camera = Graphic3d_Camera(Eye=tuple(eye), Direction=tuple(np.asarray(at) - np.asarray(eye)), Up=tuple(self.up),
-                                    FOVy=self.fovy, IsOrthographic=self.ortho, Scale=self.size or 1.0)
+                                    FOVy=self.fovy, IsOrthographic=self.ortho, Scale=self.size or auto_size or 1.0)
         fwd = np.asarray(at) - np.asarray(eye)
         fwd = fwd / np.linalg.norm(fwd)
         for l in self.lights:

@@ -153,7 +153,7 @@ class Graphic3d_RenderingParams:
     TwoSidedBsdfModels: bool = False
     CoherentPathTracingMode: bool = False
     AdaptiveScreenSampling: bool = False        # SettingsWidget.cxx:70,427-436; vrenderparams -iss
-    NbRayTracingTiles: int = 256                # OCCT default 16*16; CADRays writes 64..1024 (SettingsWidget.cxx:72,471-476)
+    NbRayTracingTiles: int = 128                # CADRays' default (SettingsWidget.cxx:72); the GUI writes 64..1024 (:471-476)
     ShowSamplingTiles: bool = False             # debug view (SettingsWidget.cxx:443-449): V3d_View.SamplingTiles()
     ToneMappingMethod: int = Graphic3d_ToneMappingMethod_Disabled
     WhitePoint: float = 1.0
@@ -266,6 +266,11 @@ class V3d_View:
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         nrm = None if nrm is None else np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
         uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        # crt_mesh_create reads 3 * n_verts normals and 2 * n_verts texels: refuse attribute arrays of another length
+        if nrm is not None and nrm.shape[0] != pos.shape[0]:
+            raise ValueError(f"normals: {nrm.shape[0]} rows for {pos.shape[0]} vertices")
+        if uv is not None and uv.shape[0] != pos.shape[0]:
+            raise ValueError(f"texels: {uv.shape[0]} rows for {pos.shape[0]} vertices")
         out = C.c_uint32()
         check(self._lib.crt_mesh_create(self._ctx, _fptr(pos), _fptr(nrm), _fptr(uv), pos.shape[0],
                                         idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.shape[0], C.byref(out)))
@@ -278,7 +283,7 @@ class V3d_View:
         return out.value
 
     def SetLocation(self, inst_id: int, trsf):
-        xf = np.ascontiguousarray(trsf, dtype=np.float32).reshape(12)
+        xf = None if trsf is None else np.ascontiguousarray(trsf, dtype=np.float32).reshape(12)   # None = identity
         check(self._lib.crt_instance_set_transform(self._ctx, int(inst_id), _fptr(xf)))
 
     def SetMaterialIndex(self, inst_id: int, material_id: int):
@@ -378,11 +383,16 @@ class V3d_View:
     def BufferDump(self, buffer_type: int = Graphic3d_BT_RGB, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Graphic3d_CView::BufferDump: RGB8 (tone-mapped) or float RGB (mean radiance), bottom-up rows."""
         w, h = self._size
+        dtype = np.uint8 if buffer_type == Graphic3d_BT_RGB else np.float32
+        if out is not None:
+            # the library writes h * w * 3 elements through this pointer
+            if not isinstance(out, np.ndarray) or out.dtype != dtype or out.shape != (h, w, 3) or not out.flags["C_CONTIGUOUS"] \
+                    or not out.flags["WRITEABLE"]:
+                raise ValueError(f"out must be a writable C-contiguous {np.dtype(dtype).name} array of shape {(h, w, 3)}")
+        img = out if out is not None else np.empty((h, w, 3), dtype=dtype)
         if buffer_type == Graphic3d_BT_RGB:
-            img = out if out is not None else np.empty((h, w, 3), dtype=np.uint8)
             check(self._lib.crt_read_ldr(self._ctx, img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
         else:
-            img = out if out is not None else np.empty((h, w, 3), dtype=np.float32)
             check(self._lib.crt_read_hdr(self._ctx, _fptr(img), 0))
         return img
 
@@ -401,12 +411,20 @@ class V3d_View:
         """V3d_View::ToPixMap(Image_PixMap&, width, height, bufferType): an off-screen render at the given size --
         resize, render `samples` (default SamplesPerPixel) samples per pixel, dump.  CADRays itself uses BufferDump on
         the live view (AppViewer.cxx:1259-1262); ToPixMap is what DRAW's `vdump -width -height` goes through."""
+        import copy
+        old_size, old_cam = self._size, copy.copy(self._camera)
         self.SetWindowSize(int(width), int(height))
-        cam = self._camera
+        cam = copy.copy(self._camera)
         cam.Aspect = float(width) / float(height)
         self.SetCamera(cam)
         self.Redraw(samples)
-        return self.BufferDump(buffer_type)
+        img = self.BufferDump(buffer_type)
+        # OCCT's ToPixMap renders into its own FBO and leaves the view as it was: restore window size and camera
+        # (the live accumulation restarts, as it does after any resize)
+        if old_size[0] and old_size[1] and old_size != (int(width), int(height)):
+            self.SetWindowSize(*old_size)
+        self.SetCamera(old_cam)
+        return img
 
     def AccumDevicePtr(self):
         p = C.c_void_p()

@@ -119,7 +119,7 @@ public:
   void SetTextureEnv(const uint8_t* rgb, uint32_t w, uint32_t h) { check(crt_envmap_set_rgb8(myCtx, rgb, w, h)); }
   void SetRenderingParams(const RenderingParams& p) { myParams = p; crt_params r = p.Record(); check(crt_params_set(myCtx, &r)); }
   const RenderingParams& RenderingParameters() const { return myParams; }
-  void SetCamera(const crt_camera& c) { check(crt_camera_set(myCtx, &c)); }
+  void SetCamera(const crt_camera& c) { myCam = c; myHasCam = true; check(crt_camera_set(myCtx, &c)); }
   void SetWindowSize(uint32_t w, uint32_t h) { check(crt_resize(myCtx, w, h)); myW = w; myH = h; }
   void Update() { check(crt_commit(myCtx)); }
   uint64_t Redraw() { uint64_t n = 0; check(crt_render(myCtx, (uint32_t)std::max(1, myParams.SamplesPerPixel), &n)); return n; }
@@ -131,12 +131,19 @@ public:
   // its pose; its aspect is set from the size), `samples` samples per pixel, RGB8 dump.  Returns false like OCCT.
   bool ToPixMap(std::vector<uint8_t>& rgb8, uint32_t w, uint32_t h, crt_camera cam, uint32_t samples)
   {
+    // OCCT renders ToPixMap into its own FBO and leaves the view untouched: window size and camera are restored
+    const uint32_t oldW = myW, oldH = myH;
+    const crt_camera oldCam = myCam;
+    const bool hadCam = myHasCam;
     SetWindowSize(w, h);
     cam.aspect = (float)w / (float)h;
     SetCamera(cam);
     uint64_t n = 0;
-    if (crt_render(myCtx, samples, &n) != CRT_OK) return false;
-    return BufferDump(rgb8);
+    bool ok = crt_render(myCtx, samples, &n) == CRT_OK;
+    ok = ok && crt_read_ldr(myCtx, (rgb8.resize((size_t)w * h * 3), rgb8.data()), 0) == CRT_OK;
+    if (oldW && oldH && (oldW != w || oldH != h)) SetWindowSize(oldW, oldH);
+    if (hadCam) SetCamera(oldCam); else { myHasCam = false; }
+    return ok;
   }
   std::vector<uint8_t> ExportBVH()
   {
@@ -148,6 +155,8 @@ private:
   crt_context* myCtx = nullptr;
   RenderingParams myParams;
   uint32_t myW = 0, myH = 0;
+  crt_camera myCam{};
+  bool myHasCam = false;
 };
 
 }  // namespace crt

@@ -457,3 +457,40 @@ def test_quad_bvh_blob(product_lib, oracle_lib):
     s = oq.trace(org, d, any_hit=True)
     assert np.array_equal(s[0] == 0, b[0] >= 0)
     v.Remove()
+
+
+def test_round1_advice_items(product_lib):
+    """Host-side argument checks the round-1 review asked for: non-finite transforms are rejected by
+    crt_instance_set_transform too, a hidden instance with a singular transform does not fail the commit,
+    attribute arrays of the wrong length never reach crt_mesh_create, BufferDump refuses a wrong `out`."""
+    v = V3d_View(host_only=True)
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    m = v.AddMesh(tri, np.array([[0, 1, 2]], np.uint32))
+    a = v.Display(m, None)
+    b = v.Display(m, scenes.trsf((0, 0, 1)))
+    bad = scenes.trsf((0, 0, 0)).copy()
+    bad[0, 3] = np.nan
+    with pytest.raises(CrtError) as e:
+        v.SetLocation(a, bad)
+    assert e.value.code == CRT_ERR_INVALID_ARG
+    v.Update()                                            # the rejected transform left nothing behind
+    v.SetLocation(b, np.zeros((3, 4), np.float32))        # singular ...
+    v.SetVisible(b, False)                                # ... but not displayed
+    v.Update()
+    v.SetVisible(b, True)
+    with pytest.raises(CrtError):
+        v.Update()                                        # displayed again: the commit refuses it
+    v.SetLocation(b, None)
+    v.Update()
+    with pytest.raises(ValueError):
+        v.AddMesh(tri, np.array([[0, 1, 2]], np.uint32), nrm=np.array([[0, 0, 1]], np.float32))
+    with pytest.raises(ValueError):
+        v.AddMesh(tri, np.array([[0, 1, 2]], np.uint32), uv=np.zeros((2, 2), np.float32))
+    v._size = (4, 4)
+    with pytest.raises(ValueError):
+        v.BufferDump(0, out=np.zeros((2, 2, 3), np.uint8))
+    with pytest.raises(ValueError):
+        v.BufferDump(0, out=np.zeros((4, 4, 3), np.float32))
+    from cadrays_b200.view import Graphic3d_RenderingParams
+    assert Graphic3d_RenderingParams().NbRayTracingTiles == 128      # SettingsWidget.cxx:72, same as the C++ mirror
+    v.Remove()
