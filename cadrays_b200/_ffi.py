@@ -105,6 +105,7 @@ PROTOTYPES = {
     "crt_accum_device_ptr": (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "crt_accum_bind": (C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
     "crt_trace": (C.c_int, [_ctx, _f, _f, _f, C.c_uint32, C.c_int, _i32, _i32, _f, _f, _f]),
+    "crt_wavefront_rays": (C.c_int, [_ctx, C.c_int, C.c_int, _f, _f, _f, C.c_uint32, C.POINTER(C.c_uint32)]),
     "crt_trace_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
     "crt_bvh_export": (C.c_int, [_ctx, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "crt_bvh_import": (C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
@@ -113,6 +114,7 @@ PROTOTYPES = {
     "crt_stats_get": (C.c_int, [_ctx, C.POINTER(crt_stats)]),
     "crt_timing_enable": (C.c_int, [_ctx, C.c_int]),
     "crt_timing_get": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "crt_scene_bytes": (C.c_int, [_ctx, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "crt_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 

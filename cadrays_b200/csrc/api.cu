@@ -96,7 +96,8 @@ struct crt_context {
   DevBuf<uint32_t> d_tex_table;
   DeviceScene ds{};
   DeviceParams dp{};
-  size_t arena_nodes = 0, arena_inst_off = 0;   // float4 offsets of the sections inside d_arena (partial re-upload)
+  size_t arena_nodes = 0, arena_inst_off = 0;
+  size_t scene_traversal_bytes = 0, scene_total_bytes = 0;   // crt_scene_bytes   // float4 offsets of the sections inside d_arena (partial re-upload)
 
   // path state
   DevBuf<float4> ray_o, ray_d, thr, rad, hit, sh_o, sh_d, sh_c;
@@ -333,6 +334,8 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
   c->ds.top_root = L.top_root;
   c->ds.scene_eps = scene_eps;
   c->quad = L.quad;
+  c->scene_traversal_bytes = (L.nodes.size() + L.tri_verts.size() + L.inst.size()) * 16;
+  c->scene_total_bytes = c->scene_traversal_bytes + L.tri_nrm.size() * 16 + L.tri_uv.size() * 4;
   if (c->l2_persist) {
     // keep nodes + triangle vertices + instance records resident in the 126 MB L2 while gigabytes of
     // path state stream past them (hit ratio scaled to the set-aside the device allows)
@@ -1211,6 +1214,45 @@ int crt_trace(crt_context* c, const float* org, const float* dir, const float* t
   return CRT_OK;
 }
 
+int crt_wavefront_rays(crt_context* c, int depth, int kind, float* org, float* dir, float* tmax, uint32_t capacity, uint32_t* out_n)
+{
+  CRT_REQUIRE(c && out_n, "null argument");
+  CRT_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (continuation rays) or 1 (shadow rays)");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if (!c->state_capacity || !c->counters.p) return fail(CRT_ERR_STATE, "crt_wavefront_rays before crt_render");
+  CRT_REQUIRE(depth >= 0 && depth < c->dp.max_depth, "depth outside the last wave");
+  CRT_REQUIRE(kind == 1 || depth >= 1, "camera rays are not stored (they are recomputed from the pixel and the frame seed)");
+  if (c->pipeline) return fail(CRT_ERR_STATE, "crt_wavefront_rays: not available with CRT_PIPELINE=1");
+  if (c->params.adaptive_sampling) return fail(CRT_ERR_STATE, "crt_wavefront_rays: not available with adaptive sampling");
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  const PathState st = make_state(c, 0, 0);
+  uint32_t n = 0;
+  CRT_CUDA(cudaMemcpy(&n, (kind ? st.n_shadow : st.n_active) + depth, sizeof n, cudaMemcpyDeviceToHost));
+  *out_n = n;
+  const uint32_t m = std::min(n, capacity);
+  if (m == 0 || (!org && !dir && !tmax)) return CRT_OK;
+  DevBuf<float4> d_o, d_d;
+  cudaError_t e = d_o.ensure(m);
+  if (e == cudaSuccess) e = d_d.ensure(m);
+  std::vector<float4> ho(m), hd(m);
+  if (e == cudaSuccess) {
+    k_gather_rays<<<grid_for(c, 8), 256, 0, c->stream>>>(st, st.queue[depth & 1], m, kind, d_o.p, d_d.p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ho.data(), d_o.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hd.data(), d_d.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  d_o.release(); d_d.release();
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? CRT_ERR_OUT_OF_MEMORY : CRT_ERR_CUDA, cudaGetErrorString(e)); }
+  for (uint32_t i = 0; i < m; ++i) {
+    if (org) { org[3 * (size_t)i] = ho[i].x; org[3 * (size_t)i + 1] = ho[i].y; org[3 * (size_t)i + 2] = ho[i].z; }
+    if (dir) { dir[3 * (size_t)i] = hd[i].x; dir[3 * (size_t)i + 1] = hd[i].y; dir[3 * (size_t)i + 2] = hd[i].z; }
+    if (tmax) tmax[i] = hd[i].w;
+  }
+  return CRT_OK;
+}
+
 int crt_bvh_export(crt_context* c, void* buf, size_t capacity, size_t* out_size)
 {
   CRT_REQUIRE(c, "null context");
@@ -1277,6 +1319,18 @@ int crt_timing_get(crt_context* c, double ms[6], uint64_t launches[6])
   CRT_CUDA(cudaStreamSynchronize(c->stream));
   collect_spans(c);
   for (int k = 0; k < F_COUNT; ++k) { ms[k] = c->family_ms[k]; if (launches) launches[k] = c->family_launches[k]; }
+  return CRT_OK;
+}
+
+int crt_scene_bytes(crt_context* c, size_t* out_traversal, size_t* out_total)
+{
+  CRT_REQUIRE(c, "null context");
+  if (!c->has_layout || c->geometry_dirty) return fail(CRT_ERR_STATE, "crt_scene_bytes before crt_commit");
+  const size_t trav = c->scene_traversal_bytes;
+  if (out_traversal) *out_traversal = trav;
+  if (out_total)
+    *out_total = c->scene_total_bytes + c->mats.size() * sizeof(crt_bsdf) + c->lights.size() * 4 + c->env.size() * 4 +
+                 c->tex_texels.size() + c->tex_table.size() * 4;
   return CRT_OK;
 }
 

@@ -1673,6 +1673,24 @@ k_display(const float4* __restrict__ accum, uint32_t n_pixels, float exposure_sc
   }
 }
 
+// crt_wavefront_rays: copies the rays of one bounce out of the path state (parity hook, not on the render path)
+__global__ void __launch_bounds__(256)
+k_gather_rays(PathState st, const uint32_t* __restrict__ q, uint32_t n, int shadow, float4* __restrict__ org, float4* __restrict__ dir)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (shadow) {
+      const float4 o = st.sh_o[i], d = st.sh_d[i];
+      org[i] = make_float4(o.x, o.y, o.z, 0.0f);
+      dir[i] = make_float4(d.x, d.y, d.z, o.w);
+    } else {
+      const uint32_t slot = q[i];
+      const float4 o = st.ray_o[slot], d = st.ray_d[slot];
+      org[i] = make_float4(o.x, o.y, o.z, 0.0f);
+      dir[i] = make_float4(d.x, d.y, d.z, CRT_MAXFLOAT);
+    }
+  }
+}
+
 template <bool ANY>
 struct TracePolicy {
   const float4* __restrict__ org;

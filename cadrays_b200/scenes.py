@@ -187,6 +187,7 @@ class SceneDesc:
     envmap: Optional[np.ndarray] = None
     textures: List[np.ndarray] = field(default_factory=list)   # uint8 (h,w,3|4), referenced by Graphic3d_BSDF.TextureId
     mesh_uvs: dict = field(default_factory=dict)                # mesh index -> (n,2) float32 texel coordinates
+    env_source: str = ""                                        # where the environment map came from (default_env)
 
     def add(self, mesh, xf=None, bsdf: Optional[Graphic3d_BSDF] = None, material_id: Optional[int] = None) -> int:
         self.meshes.append(mesh)
@@ -402,10 +403,47 @@ def synthetic_env(width=2048, height=1024) -> np.ndarray:
     return np.ascontiguousarray(img, dtype=np.float32)
 
 
-def product_shot(width=3840, height=2160, depth=12, sphere_res=(128, 64)) -> SceneDesc:
-    """Config C4: the Materials.tcl geometry lit only by a 2048x1024 environment map, 3840x2160."""
-    s = materials_scene(width, height, depth, sphere_res, env=synthetic_env())
+def default_env(path: Optional[str] = None):
+    """The environment map CADRays loads by default (data/maps/default.jpg, AppGui.cxx:963), 2048x1024, as
+    8-bit RGB (the library linearises 8-bit texels as (c/255)^2).  Looked up in this order: `path`,
+    $CADRAYS_DATA_DIR/maps/default.jpg, the reference checkout, the decoded copy of the same pixels under
+    tests/golden/ (made by tests/golden/make_default_env.py; the one that exists on a GPU box).  Returns
+    (image or None, where it came from); None = not found, callers fall back to synthetic_env()."""
+    import os
+    from pathlib import Path
+    here = Path(__file__).resolve().parent.parent
+    cands = []
+    if path:
+        cands.append((Path(path), str(path)))
+    if os.environ.get("CADRAYS_DATA_DIR"):
+        cands.append((Path(os.environ["CADRAYS_DATA_DIR"]) / "maps" / "default.jpg", "$CADRAYS_DATA_DIR/maps/default.jpg"))
+    cands.append((Path("/root/reference/data/maps/default.jpg"), "reference data/maps/default.jpg"))
+    cands.append((here / "tests" / "golden" / "default_env_2048x1024.png",
+                  "data/maps/default.jpg (decoded copy: tests/golden/default_env_2048x1024.png)"))
+    for p, what in cands:
+        if not p.exists():
+            continue
+        try:
+            from PIL import Image
+            a = np.asarray(Image.open(p).convert("RGB"))
+        except ImportError:
+            if p.suffix.lower() != ".png":
+                continue
+            from .imageio import read_png_rgb8
+            a = read_png_rgb8(str(p))
+        return np.ascontiguousarray(a, dtype=np.uint8), what
+    return None, "not found"
+
+
+def product_shot(width=3840, height=2160, depth=12, sphere_res=(128, 64), env_path: Optional[str] = None) -> SceneDesc:
+    """Config C4: the Materials.tcl geometry lit only by data/maps/default.jpg (2048x1024 lat-long), 3840x2160.
+    s.env_source says which file the map came from; the procedural sky is the fallback when none is found."""
+    env, src = default_env(env_path)
+    if env is None:
+        env, src = synthetic_env(), "synthetic sky (data/maps/default.jpg not found)"
+    s = materials_scene(width, height, depth, sphere_res, env=env)
     s.name = "product_shot"
+    s.env_source = src
     return s
 
 

@@ -435,9 +435,12 @@ class V3d_View:
     def BindAccum(self, device_ptr: Optional[int], nbytes: int = 0):
         check(self._lib.crt_accum_bind(self._ctx, C.c_void_p(device_ptr) if device_ptr else None, nbytes))
 
-    def DumpFrom(self, device_ptr: int) -> np.ndarray:
+    def DumpFrom(self, device_ptr: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         w, h = self._size
-        img = np.empty((h, w, 3), dtype=np.uint8)
+        if out is not None and (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != (h, w, 3)
+                                or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]):
+            raise ValueError(f"out must be a writable C-contiguous uint8 array of shape {(h, w, 3)}")
+        img = out if out is not None else np.empty((h, w, 3), dtype=np.uint8)
         check(self._lib.crt_read_ldr_from(self._ctx, C.c_void_p(device_ptr), img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
         return img
 
@@ -453,6 +456,17 @@ class V3d_View:
         check(self._lib.crt_trace(self._ctx, _fptr(org), _fptr(dir), _fptr(tm), n, int(any_hit),
                                   prim.ctypes.data_as(ip), inst.ctypes.data_as(ip), _fptr(t), _fptr(u), _fptr(v)))
         return prim, inst, t, u, v
+
+    def WavefrontRays(self, depth: int, shadow: bool = False):
+        """crt_wavefront_rays: (org, dir, tmax) of the rays the last wave traced at bounce `depth` -- valid when the
+        wave ran with RaytracingDepth == depth + 1 (see the header)."""
+        n = C.c_uint32()
+        check(self._lib.crt_wavefront_rays(self._ctx, int(depth), int(bool(shadow)), None, None, None, 0, C.byref(n)))
+        org = np.empty((n.value, 3), np.float32); d = np.empty((n.value, 3), np.float32); tm = np.empty(n.value, np.float32)
+        if n.value:
+            check(self._lib.crt_wavefront_rays(self._ctx, int(depth), int(bool(shadow)), _fptr(org), _fptr(d), _fptr(tm),
+                                               n.value, C.byref(n)))
+        return org, d, tm
 
     def TraceDevice(self, org4_ptr: int, dir4_ptr: int, n: int, hit4_ptr: int, inst_ptr: int = 0, any_hit: bool = False):
         check(self._lib.crt_trace_device(self._ctx, C.c_void_p(org4_ptr), C.c_void_p(dir4_ptr), int(n), int(any_hit),
@@ -489,6 +503,12 @@ class V3d_View:
         check(self._lib.crt_timing_get(self._ctx, ms, ln))
         names = ("generate", "extend", "shade", "connect", "resolve", "render")
         return {n: (ms[i], int(ln[i])) for i, n in enumerate(names)}
+
+    def SceneBytes(self):
+        """(bytes the traversal kernels read, bytes of the whole committed scene) in device memory."""
+        a, b = C.c_size_t(), C.c_size_t()
+        check(self._lib.crt_scene_bytes(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def Stream(self) -> int:
         p = C.c_void_p()

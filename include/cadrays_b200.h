@@ -293,6 +293,16 @@ int crt_trace(crt_context* ctx, const float* org, const float* dir, const float*
 int crt_trace_device(crt_context* ctx, const void* org4, const void* dir4, uint32_t n,
                      int any_hit, void* hit4 /* float4 t,u,v,prim-bits */, void* inst_i32);
 
+/* The rays the LAST wave of crt_render traced at bounce `depth` (read back from the path
+ * state; n x 3 floats each, tmax n floats; any output may be NULL; out_n = how many exist, at
+ * most `capacity` are copied).  kind 0: continuation rays entering bounce `depth` (closest-hit
+ * queries), kind 1: the shadow rays bounce `depth` emitted (any-hit queries, tmax = light
+ * distance).  The wavefront reuses its buffers from bounce to bounce, so the rays of bounce
+ * `depth` are intact only when the wave ran with crt_params.max_depth == depth + 1.
+ * Parity tests feed these real secondary rays to crt_trace and to the oracle. */
+int crt_wavefront_rays(crt_context* ctx, int depth, int kind, float* org, float* dir, float* tmax,
+                       uint32_t capacity, uint32_t* out_n);
+
 /* Flattened two-level BVH + geometry exactly as the kernels walk it, so the CPU
  * oracle can traverse identical bytes.  Call with buf = NULL to query the size. */
 int crt_bvh_export(crt_context* ctx, void* buf, size_t capacity, size_t* out_size);
@@ -308,6 +318,10 @@ int crt_stats_get(crt_context* ctx, crt_stats* out);
  * Only collected while crt_timing_enable(ctx, 1). */
 int crt_timing_enable(crt_context* ctx, int on);
 int crt_timing_get(crt_context* ctx, double ms[6], uint64_t launches[6]);
+/* Bytes of the committed scene in device memory: `traversal` = what SceneNearestHit / SceneAnyHit read (nodes,
+ * triangle vertices, instance records), `total` adds the shading-side arrays (vertex normals, texels, materials,
+ * lights, textures, environment).  The bench sizes its L2 / HBM probe with the first. */
+int crt_scene_bytes(crt_context* ctx, size_t* out_traversal, size_t* out_total);
 /* CUDA stream of the context as an opaque cudaStream_t. */
 int crt_stream(crt_context* ctx, void** out_stream);
 

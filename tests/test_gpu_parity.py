@@ -282,29 +282,100 @@ def test_error_behaviour(product_lib):
     view.Remove()
 
 
-# ------------------------------------------------------------------ full-size properties (BASELINE config C2)
+# ------------------------------------------------------------------ full-size parity: every BASELINE config at its stated size
 
-def test_full_size_properties(product_lib):
-    """1080p, depth 8, ~1M triangles: size-independent properties where the oracle is too slow."""
-    desc = scenes.assembly()           # config C2
-    assert abs(desc.n_triangles() - 1_000_000) <= 10_000 + 2
-    view = V3d_View(0)
-    desc.apply(view)
-    view.Redraw(2)
-    a = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft).copy()
-    assert np.isfinite(a).all() and a.max() > 0 and (a >= 0).all()
-    view.ResetAccumulation(0)
-    view.Redraw(2)
-    b = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
-    assert np.array_equal(a, b), "rendering must be deterministic"
-    # any-hit agrees with closest-hit on 1M random rays
+FULL_SIZE = {
+    # resolution, depth, geometry and lights as stated there
+    "C1_cornell": lambda: scenes.cornell_box(512, 512, depth=5),                      # CornellBox.tcl:76 uses -rayDepth 5
+    "C2_assembly": lambda: scenes.assembly(),                                         # 1920x1080, depth 8, 999 992 triangles
+    "C3_materials": lambda: scenes.materials_scene(1920, 1080, depth=12),             # Materials.tcl:10-37,203; spheres 128x64
+    "C4_product_shot": lambda: scenes.product_shot(3840, 2160, depth=8),              # lit only by data/maps/default.jpg
+    "C5_instanced": lambda: scenes.instanced(),                                       # 1024 instances of 16 meshes, 10.5 M triangles
+    "C5_flattened": lambda: scenes.instanced(n_meshes=1024),                          # 10.5 M unique triangles
+}
+
+
+def _assert_hits_equal(g, o, what):
+    ties = int(np.sum((g[0] != o[0]) & (g[2] == o[2])))
+    assert np.array_equal(g[0], o[0]), f"{what}: primitive ids differ on {int(np.sum(g[0] != o[0]))} rays ({ties} exact-distance ties)"
+    assert np.array_equal(g[1], o[1]), f"{what}: instance ids differ"
+    hit = g[0] >= 0
+    assert np.array_equal(g[2], o[2]) and np.array_equal(g[3][hit], o[3][hit]) and np.array_equal(g[4][hit], o[4][hit]), f"{what}: t/u/v differ"
+
+
+@pytest.mark.parametrize("cfg", list(FULL_SIZE))
+def test_full_size_parity(cfg, product_lib, oracle_lib):
+    """Levels 1 and 2 of the north_star at the size BASELINE.md states for the config, against the oracle on the same
+    BVH bytes: (1) 1 M random rays plus every real bounce-1 continuation and shadow ray of a 1-spp frame, read back
+    from the wavefront (crt_wavefront_rays) -- primitive / instance ids, t, u, v, any-hit answers and the traversal
+    work counters bit-equal, exact-distance ties counted in the message; (2) one full-resolution 1-spp frame at the
+    config's depth, bit-equal (stated bound 1e-4)."""
+    import copy
     import struct
+    desc = FULL_SIZE[cfg]()
+    if cfg == "C4_product_shot":
+        assert desc.envmap is not None and desc.envmap.dtype == np.uint8 and desc.envmap.shape == (1024, 2048, 3), desc.env_source
+        assert "default" in desc.env_source and not desc.lights
+    if cfg == "C2_assembly":
+        assert abs(desc.n_triangles() - 1_000_000) <= 10_000 + 2
+    if cfg.startswith("C5"):
+        assert desc.n_triangles() >= 10_000_000 and len(desc.instances) >= 1024
+    view, orc = _pair(desc)
+    w, h = desc.width, desc.height
+    # ---- level 1a: random rays through the scene box
     hdr = struct.unpack_from("<8I7f", view.ExportBVH(), 0)
     org, d = scenes.random_rays(1_000_000, hdr[8:11], hdr[11:14], seed=21)
-    n = view.Trace(org, d)
+    view.EnableStats(True); view.ResetStats()
+    g = view.Trace(org, d)
+    gs = view.Stats()
+    view.EnableStats(False)
+    o = orc.trace(org, d, stats=True)
+    _assert_hits_equal(g, o, "random rays")
+    for k in ("rays_nearest", "n_inner", "n_leaf", "n_tri", "n_switch"):
+        assert gs[k] == o[5][k], k
     s = view.Trace(org, d, any_hit=True)
-    assert np.array_equal(n[0] >= 0, s[0] == 0)
+    assert np.array_equal(s[0], orc.trace(org, d, any_hit=True)[0]) and np.array_equal(g[0] >= 0, s[0] == 0)
+    # ---- level 1b: the real secondary rays of one frame (a wave that stops after bounce 1 keeps them in the path state)
+    p2 = copy.copy(desc.params)
+    p2.RaytracingDepth = 2
+    p2.SamplesPerBatch = 1
+    view.SetRenderingParams(p2)
+    view.Redraw(1)
+    co, cd, _ = view.WavefrontRays(1, shadow=False)
+    so, sd, st = view.WavefrontRays(1, shadow=True)
+    assert co.shape[0] + so.shape[0] >= (250_000 if cfg == "C1_cornell" else 1_000_000), (co.shape, so.shape)
+    view.EnableStats(True); view.ResetStats()
+    g = view.Trace(co, cd)
+    gs = view.Stats()
+    view.EnableStats(False)
+    o = orc.trace(co, cd, stats=True)
+    _assert_hits_equal(g, o, "bounce-1 continuation rays")
+    for k in ("rays_nearest", "n_inner", "n_leaf", "n_tri", "n_switch"):
+        assert gs[k] == o[5][k], k
+    view.EnableStats(True); view.ResetStats()
+    ga = view.Trace(so, sd, st, any_hit=True)
+    gs = view.Stats()
+    view.EnableStats(False)
+    oa = orc.trace(so, sd, st, any_hit=True, stats=True)
+    assert np.array_equal(ga[0], oa[0]), "bounce-1 shadow rays"
+    for k in ("rays_any", "n_inner_any", "n_leaf_any", "n_tri_any", "n_switch_any"):
+        assert gs[k] == oa[5][k], k
+    # ---- level 2: one full-resolution sample per pixel at the config's depth
+    view.SetRenderingParams(desc.params)
+    orc.set_params(desc.params)
+    view.ResetAccumulation(0)
+    view.Redraw(1)
+    gi = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    oi = orc.hdr(orc.render(w, h, 1))
+    assert np.isfinite(gi).all() and gi.max() > 0
+    assert float(np.abs(gi - oi).max()) <= LEVEL2_TOL
+    assert np.array_equal(gi, oi), f"{int(np.sum(np.any(gi != oi, axis=2)))} of {w * h} pixels differ"
+    # determinism and batching independence at full size
+    view.ResetAccumulation(0)
+    view.Redraw(1)
+    assert np.array_equal(gi, view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft))
     view.Remove()
+    orc.close()
 
 
 # ------------------------------------------------------------------ SURVEY 8(f): script loader + headless run
@@ -362,18 +433,22 @@ foreach aMat {gold jade glass} {
     assert (tmp_path / "Output_Icons_2.png").exists()
 
 
-def test_level3_converged_4096spp(product_lib, oracle_lib):
-    """north_star level 3: converged 4096-spp images.  Stated bound: per-pixel relative error <= 1e-5 and
-    RMSE <= 1e-6 of the mean; measured: bit-equal (same sample set, same summation order)."""
-    desc = scenes.cornell_box(24, 16, depth=5, sphere_res=(16, 8))
+@pytest.mark.parametrize("which", ["C1_cornell", "C3_materials"])
+def test_level3_converged_4096spp(which, product_lib, oracle_lib):
+    """north_star level 3: converged 4096-spp images of C1 (CornellBox.tcl, -rayDepth 5) and C3 (Materials.tcl, depth
+    12) on a 256x144 window.  Stated bound: per-pixel relative error <= 1e-5 and RMSE <= 1e-6 of the mean; measured:
+    bit-equal (same sample set, same summation order)."""
+    desc = scenes.cornell_box(256, 144, depth=5) if which == "C1_cornell" else scenes.materials_scene(256, 144, depth=12)
     view, orc = _pair(desc)
-    view.Redraw(4096)
+    assert view.Redraw(4096) == 4096
     g = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
-    o = orc.hdr(orc.render(24, 16, 4096))
+    o = orc.hdr(orc.render(256, 144, 4096))
     rel = np.abs(g - o) / np.maximum(np.abs(o), 1e-6)
     assert rel.max() <= 1e-5 and float(np.sqrt(np.mean((g - o) ** 2))) <= 1e-6 * float(o.mean())
     assert np.array_equal(g, o)
+    assert np.array_equal(view.BufferDump(Graphic3d_BT_RGB), orc.display(orc.render(256, 144, 4096)))
     view.Remove()
+    orc.close()
 
 
 def test_textured_scene_parity(product_lib, oracle_lib):
