@@ -116,6 +116,17 @@ PROTOTYPES = {
     "crt_timing_get": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "crt_scene_bytes": (C.c_int, [_ctx, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "crt_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
+    "crt_commit_stats": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
+    "crt_group_create": (C.c_int, [_ctx, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "crt_group_destroy": (None, [C.c_void_p]),
+    "crt_group_size": (C.c_int, [C.c_void_p]),
+    "crt_group_member": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_ctx)]),
+    "crt_group_commit": (C.c_int, [C.c_void_p]),
+    "crt_group_render": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "crt_group_reset_accumulation": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "crt_group_read_ldr": (C.c_int, [C.c_void_p, _u8, C.c_size_t]),
+    "crt_group_read_hdr": (C.c_int, [C.c_void_p, _f, C.c_size_t]),
+    "crt_group_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
 }
 
 _lib = None

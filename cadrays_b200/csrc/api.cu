@@ -76,6 +76,7 @@ struct crt_context {
   bool geometry_dirty = true;
   std::vector<uint8_t> blob;
   bool has_layout = false;
+  bool blob_on_device = false;       // the device layout was converted from `blob` as it stands (top-level patches apply)
   bool quad = false;                 // the uploaded layout is the 4-wide one (crt_params.bvh_width = 4)
   std::vector<crt_bsdf> mats;
   std::vector<float> lights;         // 8 floats per light, shader form
@@ -96,8 +97,12 @@ struct crt_context {
   DevBuf<uint32_t> d_tex_table;
   DeviceScene ds{};
   DeviceParams dp{};
-  size_t arena_nodes = 0, arena_inst_off = 0;
-  size_t scene_traversal_bytes = 0, scene_total_bytes = 0;   // crt_scene_bytes   // float4 offsets of the sections inside d_arena (partial re-upload)
+  size_t arena_nodes = 0, arena_inst_off = 0;                // float4 offsets of the sections inside d_arena (partial re-upload)
+  size_t scene_traversal_bytes = 0, scene_total_bytes = 0;   // crt_scene_bytes
+  DeviceLayout layout_info;          // the uploaded layout without its big arrays (counts, depths, mesh_root_ref)
+  uint64_t top_patches = 0;          // commits that re-uploaded the top-level nodes + instance records only
+  // change counters: crt_group replicates what changed on the other GPUs of the group
+  uint64_t gen_scene = 0, gen_mats = 0, gen_lights = 0, gen_env = 0, gen_tex = 0, gen_accum = 0;
 
   // path state
   DevBuf<float4> ray_o, ray_d, thr, rad, hit, sh_o, sh_d, sh_c;
@@ -210,6 +215,7 @@ void reset_accum_state(crt_context* c)
 {
   c->next_sample = c->first_sample;
   c->ad_clear = true;
+  c->gen_accum++;
   if (c->device >= 0 && c->accum && c->width && c->height)
     cudaMemsetAsync(c->accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream);
 }
@@ -358,15 +364,62 @@ int upload_layout(crt_context* c, const DeviceLayout& L, float scene_eps)
     }
   }
   c->has_layout = true;
+  c->gen_scene++;
+  c->layout_info = DeviceLayout{};
+  c->layout_info.top_root = L.top_root; c->layout_info.n_tris = L.n_tris; c->layout_info.n_inst = L.n_inst;
+  c->layout_info.n_top_inner = L.n_top_inner; c->layout_info.quad = L.quad;
+  c->layout_info.max_depth_top = L.max_depth_top; c->layout_info.max_depth_bottom = L.max_depth_bottom;
+  c->layout_info.mesh_root_ref = L.mesh_root_ref;
   return CRT_OK;
 }
 
-int load_blob(crt_context* c)
+// Device side of an instance-only edit (SetLocation, ImRaytraceControls.cxx:88; material assignment,
+// MaterialEditor.cxx:522-523): `T` holds the re-emitted top-level nodes and the instance records; the bottom
+// trees, triangles and normals already on the device are left alone (about 200 KB instead of 120 MB for the
+// 1 M-triangle assembly).
+int upload_layout_top(crt_context* c, const DeviceLayout& T, float scene_eps)
+{
+  if (T.max_depth_top + T.max_depth_bottom + 4 > kStackSize) return fail(CRT_ERR_FORMAT, "BVH deeper than the traversal stack");
+  if (T.nodes.size() > c->arena_nodes || T.inst.size() > c->d_arena.n - c->arena_inst_off)
+    return fail(CRT_ERR_STATE, "top-level patch does not fit the uploaded layout");
+  CRT_CUDA(cudaStreamSynchronize(c->stream));       // no kernel still walks the records about to change
+  float4* nodes = c->d_arena.p;
+  float4* inst = c->d_arena.p + c->arena_inst_off;
+  if (!T.nodes.empty()) CRT_CUDA(cudaMemcpyAsync(nodes, T.nodes.data(), T.nodes.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  if (!T.inst.empty()) CRT_CUDA(cudaMemcpyAsync(inst, T.inst.data(), T.inst.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  const uint32_t n_cache = std::min<uint32_t>(T.n_top_inner, 1024u);
+  std::vector<f4> cache((size_t)5 * std::max<uint32_t>(n_cache, 1), f4{ 0, 0, 0, 0 });
+  for (uint32_t k = 0; k < n_cache; ++k)
+    for (int q = 0; q < 4; ++q) cache[5 * (size_t)k + q] = T.nodes[4 * (size_t)k + q];
+  if (cache.size() <= c->d_top_cache.n)
+    CRT_CUDA(cudaMemcpyAsync(c->d_top_cache.p, cache.data(), cache.size() * 16, cudaMemcpyHostToDevice, c->stream));
+  CRT_CUDA(cudaStreamSynchronize(c->stream));
+  c->ds.top_root = T.top_root;
+  c->ds.scene_eps = scene_eps;
+  c->layout_info.top_root = T.top_root;
+  c->layout_info.max_depth_top = T.max_depth_top;
+  c->top_patches++;
+  c->gen_scene++;
+  return CRT_OK;
+}
+
+// `patched`: build_blob rewrote only the header, the top-level nodes and the instance records of the blob this
+// context's device layout came from, so the device copy is patched the same way; `keep` (optional) receives the
+// layout that was uploaded so that crt_group can upload it to the other GPUs without converting the blob again.
+int load_blob(crt_context* c, bool patched = false, DeviceLayout* keep = nullptr, bool* keep_is_top = nullptr)
 {
   BlobView view;
   std::string err;
   if (!parse_blob(c->blob.data(), c->blob.size(), view, err)) return fail(CRT_ERR_FORMAT, err);
-  DeviceLayout L;
+  DeviceLayout local;
+  DeviceLayout& L = keep ? *keep : local;
+  if (keep_is_top) *keep_is_top = false;
+  if (patched && c->has_layout && !c->quad && build_device_layout_top(view, c->layout_info, L, err)) {
+    const int rc = upload_layout_top(c, L, view.hdr.scene_eps);
+    if (rc == CRT_OK) { if (keep_is_top) *keep_is_top = true; return rc; }
+    if (rc != CRT_ERR_STATE) return rc;
+  }
+  err.clear();
   if (!build_device_layout(view, L, err)) return fail(CRT_ERR_FORMAT, err);
   return upload_layout(c, L, view.hdr.scene_eps);
 }
@@ -409,6 +462,24 @@ int upload_tables(crt_context* c)
     c->env_dirty = false;
   }
   CRT_CUDA(cudaStreamSynchronize(c->stream));
+  return CRT_OK;
+}
+
+// host BVH build (or in-place patch of the previous blob) + device upload, when the geometry changed
+int commit_geometry(crt_context* c, DeviceLayout* keep, bool* keep_is_top)
+{
+  if (!c->geometry_dirty) return CRT_OK;
+  std::string err;
+  const uint64_t patched_before = c->scene.blobs_patched;
+  const bool same_blob = c->blob_on_device;      // the device layout was made from c->blob as it is now
+  if (!build_blob(c->scene, c->blob, err, c->params.bvh_width == 4 ? 4 : 2)) { c->blob_on_device = false; return fail(CRT_ERR_INVALID_ARG, err); }
+  const bool patched = same_blob && c->scene.blobs_patched != patched_before;
+  c->blob_on_device = false;
+  const int rc = load_blob(c, patched, keep, keep_is_top);
+  if (rc) return rc;
+  c->blob_on_device = true;
+  c->geometry_dirty = false;
+  reset_accum_state(c);
   return CRT_OK;
 }
 
@@ -853,6 +924,7 @@ int crt_materials_set(crt_context* c, const crt_bsdf* b, uint32_t n)
   CRT_REQUIRE(c && (b || n == 0), "null argument");
   c->mats.assign(b, b + n);
   c->mats_dirty = true;
+  c->gen_mats++;
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -867,6 +939,7 @@ int crt_texture_create(crt_context* c, const uint8_t* rgba8, uint32_t w, uint32_
   c->tex_table.push_back((uint32_t)offset); c->tex_table.push_back(w); c->tex_table.push_back(h);
   *out_id = (uint32_t)(c->tex_table.size() / 3) - 1;
   c->tex_dirty = true;
+  c->gen_tex++;
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -876,6 +949,7 @@ int crt_textures_clear(crt_context* c)
   CRT_REQUIRE(c, "null context");
   c->tex_texels.clear(); c->tex_table.clear();
   c->tex_dirty = true;
+  c->gen_tex++;
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -897,6 +971,7 @@ int crt_lights_set(crt_context* c, const crt_light* l, uint32_t n)
     }
   }
   c->lights_dirty = true;
+  c->gen_lights++;
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -913,6 +988,7 @@ int crt_envmap_set_rgb32f(crt_context* c, const float* rgb, uint32_t w, uint32_t
     c->env_w = w; c->env_h = h;
   }
   c->env_dirty = true;
+  c->gen_env++;
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -977,13 +1053,7 @@ int crt_commit(crt_context* c)
   }
   int rc = set_device(c);
   if (rc) return rc;
-  if (c->geometry_dirty) {
-    std::string err;
-    if (!build_blob(c->scene, c->blob, err, c->params.bvh_width == 4 ? 4 : 2)) return fail(CRT_ERR_INVALID_ARG, err);
-    if ((rc = load_blob(c))) return rc;
-    c->geometry_dirty = false;
-    reset_accum_state(c);
-  }
+  if ((rc = commit_geometry(c, nullptr, nullptr))) return rc;
   return upload_tables(c);
 }
 
@@ -1272,6 +1342,7 @@ int crt_bvh_import(crt_context* c, const void* buf, size_t size)
   std::vector<uint8_t> keep(static_cast<const uint8_t*>(buf), static_cast<const uint8_t*>(buf) + size);
   c->blob.swap(keep);
   c->scene.blob_signature.clear();      // the blob no longer comes from this context's scene
+  c->blob_on_device = false;
   rc = load_blob(c);
   if (rc) {
     c->blob.swap(keep);
@@ -1280,6 +1351,7 @@ int crt_bvh_import(crt_context* c, const void* buf, size_t size)
     return rc;
   }
   c->geometry_dirty = false;
+  c->blob_on_device = false;            // an imported blob is not the scene's: the next crt_commit converts in full
   reset_accum_state(c);
   return CRT_OK;
 }
@@ -1334,6 +1406,13 @@ int crt_scene_bytes(crt_context* c, size_t* out_traversal, size_t* out_total)
   return CRT_OK;
 }
 
+int crt_commit_stats(crt_context* c, uint64_t* out_top_level_patches)
+{
+  CRT_REQUIRE(c, "null context");
+  if (out_top_level_patches) *out_top_level_patches = c->top_patches;
+  return CRT_OK;
+}
+
 int crt_stream(crt_context* c, void** out_stream)
 {
   CRT_REQUIRE(c && out_stream, "null argument");
@@ -1342,3 +1421,5 @@ int crt_stream(crt_context* c, void** out_stream)
 }
 
 }  // extern "C"
+
+#include "group.inl"

@@ -623,8 +623,8 @@ struct Converter {
   std::string& err;
   bool ok = true;
   std::unordered_map<int32_t, int32_t> mesh_root_ref;   // bottom root node -> device ref
-  std::unordered_map<int32_t, int>     mesh_root_depth;
   int cur_depth_max = 0;
+  bool top_only = false;   // build_device_layout_top: bottom trees are on the device already, mesh_root_ref is given
 
   bool node_ok(int64_t n) const { return n >= 0 && n < (int64_t)v.hdr.n_nodes; }
 
@@ -710,6 +710,7 @@ struct Converter {
     int32_t ref;
     auto it = mesh_root_ref.find(info[1]);
     if (it == mesh_root_ref.end()) {
+      if (top_only) { err = "top-level patch: unknown bottom tree"; ok = false; return kRefNone; }
       cur_depth_max = 0;
       ref = out.quad ? quad_node(info[1], info[1], info[3], false, 0) : bottom(info[1], info[1], info[3], 0);
       mesh_root_ref[info[1]] = ref;
@@ -830,7 +831,34 @@ bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err)
   out.quad = (h.flags & 2u) != 0;
   Converter c{ v, out, err };
   out.top_root = out.quad ? c.quad_node(0, 0, 0, true, 0) : c.top(0);
+  out.mesh_root_ref.assign(c.mesh_root_ref.begin(), c.mesh_root_ref.end());
   return c.ok;
+}
+
+// The top-level half of build_device_layout for a blob whose mesh sections did not change since `prev` was built
+// (build_blob patched it in place: an object moved, changed its material or -- with the same number of visible
+// objects -- its visibility): top-level nodes in breadth-first order and the instance records, nothing else.
+bool build_device_layout_top(const BlobView& v, const DeviceLayout& prev, DeviceLayout& out, std::string& err)
+{
+  out = DeviceLayout{};
+  const BlobHeader& h = v.hdr;
+  if (prev.quad || (h.flags & 2u) || h.n_nodes == 0 || h.n_inst == 0 || h.n_tris != prev.n_tris) return false;
+  out.n_tris = h.n_tris;
+  out.n_inst = h.n_inst;
+  out.max_depth_bottom = prev.max_depth_bottom;
+  out.inst.assign(4 * (size_t)h.n_inst, f4{ 0, 0, 0, 0 });
+  for (size_t k = 0; k < h.n_inst; ++k) {
+    const float* m = v.inst_inv + 16 * k;
+    for (int r = 0; r < 3; ++r) out.inst[4 * k + r] = f4{ m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3] };
+    out.inst[4 * k + 3] = f4{ Converter::bits(kRefNone), Converter::bits(v.inst_meta[4 * k]), 0.0f, 0.0f };
+  }
+  Converter c{ v, out, err };
+  c.top_only = true;
+  c.mesh_root_ref.insert(prev.mesh_root_ref.begin(), prev.mesh_root_ref.end());
+  out.top_root = c.top(0);
+  if (!c.ok || out.n_top_inner != prev.n_top_inner) return false;
+  out.mesh_root_ref = prev.mesh_root_ref;
+  return true;
 }
 
 }  // namespace crt

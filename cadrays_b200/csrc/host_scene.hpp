@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace crt {
@@ -137,8 +138,16 @@ struct DeviceLayout {
   // then (ref0..ref3) as int bits (kRefNone = no such child), then one pad float4
   bool quad = false;
   int max_depth_top = 0, max_depth_bottom = 0;
+  // blob index of a mesh's bottom root node -> device reference of its converted tree (kept so that a commit
+  // after an instance-only edit can re-emit the top level without touching the bottom trees)
+  std::vector<std::pair<int32_t, int32_t>> mesh_root_ref;
 };
 
 bool build_device_layout(const BlobView& v, DeviceLayout& out, std::string& err);
+// Top-level nodes + instance records only (out.nodes = the n_top_inner top nodes, out.inst, out.top_root), for a
+// blob that differs from the one `prev` was built from in its header, top-level nodes and instance records only.
+// Returns false when the shortcut does not apply (4-wide layout, different top-level node count, unknown mesh):
+// the caller then builds the full layout.
+bool build_device_layout_top(const BlobView& v, const DeviceLayout& prev, DeviceLayout& out, std::string& err);
 
 }  // namespace crt

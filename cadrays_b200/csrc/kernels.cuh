@@ -1651,25 +1651,55 @@ __device__ __forceinline__ float filmic(float c)
   return (fmaf(c, f, 0.004f)) / (fmaf(c, f + 0.55f, 0.0491f)) - 0.0821f;
 }
 
+// one pixel of the Display pass: mean of the sums, exposure, optional filmic curve, gamma 2, RGB8 rounding
+__device__ __forceinline__ void display_pixel(const float4 a, uint32_t i, float exposure_scale, int tone_map, float wp_curve,
+                                              uint8_t* __restrict__ rgb8, float* __restrict__ rgb32f)
+{
+  const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+  const float m[3] = { a.x * inv, a.y * inv, a.z * inv };
+  if (rgb32f) { rgb32f[3 * (size_t)i] = m[0]; rgb32f[3 * (size_t)i + 1] = m[1]; rgb32f[3 * (size_t)i + 2] = m[2]; }
+  if (rgb8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = m[c] * exposure_scale;
+      if (tone_map) x = filmic(x) / wp_curve;
+      x = sqrtf(maxf(x, 0.0f));
+      x = minf(x, 1.0f);
+      rgb8[3 * (size_t)i + c] = (uint8_t)(int)fmaf(x, 255.0f, 0.5f);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_display(const float4* __restrict__ accum, uint32_t n_pixels, float exposure_scale, int tone_map, float wp_curve,
           uint8_t* __restrict__ rgb8, float* __restrict__ rgb32f)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
-    const float4 a = accum[i];
-    const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
-    const float m[3] = { a.x * inv, a.y * inv, a.z * inv };
-    if (rgb32f) { rgb32f[3 * (size_t)i] = m[0]; rgb32f[3 * (size_t)i + 1] = m[1]; rgb32f[3 * (size_t)i + 2] = m[2]; }
-    if (rgb8) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float x = m[c] * exposure_scale;
-        if (tone_map) x = filmic(x) / wp_curve;
-        x = sqrtf(maxf(x, 0.0f));
-        x = minf(x, 1.0f);
-        rgb8[3 * (size_t)i + c] = (uint8_t)(int)fmaf(x, 255.0f, 0.5f);
-      }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x)
+    display_pixel(accum[i], i, exposure_scale, tone_map, wp_curve, rgb8, rgb32f);
+}
+
+// Multi-GPU Redraw (crt_group): the exchange step and the Display pass in ONE kernel.  Every GPU of the group holds
+// the sample sums of its own sample range; GPU r of the group runs this kernel over rows [first, first + count) of
+// the frame, loads the float4 sums of that slice from every member's accumulation buffer through NVLink peer
+// addresses (plain ld.global on a peer pointer), adds them in member order -- a fixed order, so the image does not
+// depend on which GPU reduced which slice -- and writes the tone-mapped pixels.  No intermediate sum buffer, no
+// second pass: 16 B x members read per pixel, 3 B written.
+constexpr int kMaxGroup = 16;
+struct PeerAccums { const float4* p[kMaxGroup]; int n; };
+
+__global__ void __launch_bounds__(256)
+k_display_peers(PeerAccums A, uint32_t first, uint32_t count, float exposure_scale, int tone_map, float wp_curve,
+                uint8_t* __restrict__ rgb8, float* __restrict__ rgb32f, float4* __restrict__ sum_out)
+{
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const uint32_t i = first + k;
+    float4 a = A.p[0][i];
+    for (int r = 1; r < A.n; ++r) {
+      const float4 b = A.p[r][i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
+    if (sum_out) sum_out[i] = a;
+    display_pixel(a, i, exposure_scale, tone_map, wp_curve, rgb8, rgb32f);
   }
 }
 

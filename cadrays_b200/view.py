@@ -230,25 +230,65 @@ def _fptr(a: Optional[np.ndarray]):
 
 
 class V3d_View:
-    """One render target on one GPU: owns a crt_context."""
+    """One render target: owns a crt_context on `device`.  With `devices=[d0, d1, ...]` (d0 = the view's own
+    device) the same view drives every listed GPU from this one process through a crt_group: Update(), Redraw(),
+    BufferDump() and ResetAccumulation() go to the group, everything else (scene, materials, lights, camera,
+    parameters) is set on the view as before and replicated by the library."""
 
-    def __init__(self, device: int = 0, host_only: bool = False):
+    def __init__(self, device: int = 0, host_only: bool = False, devices: Optional[Sequence[int]] = None):
         self._lib = _ffi.load_library()
         self._ctx = C.c_void_p()
+        self._group = C.c_void_p()
+        if devices is not None and len(devices):
+            device = int(devices[0])
         if host_only:
             check(self._lib.crt_create_host_only(C.byref(self._ctx)))
         else:
             check(self._lib.crt_create(int(device), C.byref(self._ctx)))
+        if devices is not None and len(devices) and not host_only:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            try:
+                check(self._lib.crt_group_create(self._ctx, arr, len(devices), C.byref(self._group)))
+            except Exception:
+                self._lib.crt_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+                raise
         self._params = Graphic3d_RenderingParams()
         self._camera = Graphic3d_Camera()
         self._size = (0, 0)
         self.device = device
+        self.devices = [int(d) for d in devices] if devices is not None and len(devices) else [int(device)]
 
     # -- lifetime
     def Remove(self):
+        if self._group:
+            self._lib.crt_group_destroy(self._group)
+            self._group = C.c_void_p()
         if self._ctx:
             self._lib.crt_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+    def GroupInfo(self) -> dict:
+        """crt_group_info: peer access, NCCL path in use, device ms of the last exchange + Display pass."""
+        if not self._group:
+            return {"members": 1, "peer_access": True, "nccl": False, "reduce_ms": 0.0}
+        a, b, ms = C.c_int(), C.c_int(), C.c_double()
+        check(self._lib.crt_group_info(self._group, C.byref(a), C.byref(b), C.byref(ms)))
+        return {"members": self._lib.crt_group_size(self._group), "peer_access": bool(a.value), "nccl": bool(b.value),
+                "reduce_ms": ms.value}
+
+    def MemberHandle(self, rank: int):
+        if not self._group:
+            return self._ctx
+        out = C.c_void_p()
+        check(self._lib.crt_group_member(self._group, int(rank), C.byref(out)))
+        return out
+
+    def CommitStats(self) -> int:
+        """How many Update() calls re-uploaded the top-level nodes + instance records only."""
+        n = C.c_uint64()
+        check(self._lib.crt_commit_stats(self._ctx, C.byref(n)))
+        return n.value
 
     def __del__(self):
         try:
@@ -358,14 +398,20 @@ class V3d_View:
 
     def Update(self):
         """Explicit form of OCCT's state-counter invalidation: BVH (re)build + upload."""
-        check(self._lib.crt_commit(self._ctx))
+        if self._group:
+            check(self._lib.crt_group_commit(self._group))
+        else:
+            check(self._lib.crt_commit(self._ctx))
 
     # -- render
     def Redraw(self, samples: Optional[int] = None) -> int:
         """V3d_View::Redraw(): adds SamplesPerPixel samples (or `samples`); returns the total."""
         n = int(self._params.SamplesPerPixel if samples is None else samples)
         total = C.c_uint64()
-        check(self._lib.crt_render(self._ctx, n, C.byref(total)))
+        if self._group:
+            check(self._lib.crt_group_render(self._group, n, C.byref(total)))
+        else:
+            check(self._lib.crt_render(self._ctx, n, C.byref(total)))
         return total.value
 
     def RedrawAsync(self, samples: int):
@@ -375,7 +421,10 @@ class V3d_View:
         check(self._lib.crt_sync(self._ctx))
 
     def ResetAccumulation(self, first_sample: int = 0):
-        check(self._lib.crt_reset_accumulation(self._ctx, int(first_sample)))
+        if self._group:
+            check(self._lib.crt_group_reset_accumulation(self._group, int(first_sample)))
+        else:
+            check(self._lib.crt_reset_accumulation(self._ctx, int(first_sample)))
 
     def SetNextSample(self, index: int):
         check(self._lib.crt_set_next_sample(self._ctx, int(index)))
@@ -390,7 +439,12 @@ class V3d_View:
                     or not out.flags["WRITEABLE"]:
                 raise ValueError(f"out must be a writable C-contiguous {np.dtype(dtype).name} array of shape {(h, w, 3)}")
         img = out if out is not None else np.empty((h, w, 3), dtype=dtype)
-        if buffer_type == Graphic3d_BT_RGB:
+        if self._group:
+            if buffer_type == Graphic3d_BT_RGB:
+                check(self._lib.crt_group_read_ldr(self._group, img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
+            else:
+                check(self._lib.crt_group_read_hdr(self._group, _fptr(img), 0))
+        elif buffer_type == Graphic3d_BT_RGB:
             check(self._lib.crt_read_ldr(self._ctx, img.ctypes.data_as(C.POINTER(C.c_uint8)), 0))
         else:
             check(self._lib.crt_read_hdr(self._ctx, _fptr(img), 0))

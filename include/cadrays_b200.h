@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CRT_ABI_VERSION 2
+#define CRT_ABI_VERSION 3
 
 typedef enum crt_status {
   CRT_OK               =  0,
@@ -278,6 +278,44 @@ int crt_accum_bind(crt_context* ctx, void* device_ptr, size_t bytes);
  * context's LDR/HDR read-back path. */
 int crt_read_ldr_from(crt_context* ctx, const void* device_accum, uint8_t* rgb8, size_t stride_bytes);
 
+/* ------------------------- several GPUs, one host process ------------------------ */
+
+/* CADRays is one C++ process that calls V3d_View::Redraw() (src/Launcher/AppViewer.cxx:1047) and
+ * BufferDump (AppViewer.cxx:1259-1262) from the thread that owns the view.  A group lets that one call
+ * drive every GPU of the box: `primary` (the context the host already fills with meshes, materials,
+ * lights, parameters and camera -- it stays the only one the host talks to) becomes member 0, and the
+ * group creates one replica context per further entry of `devices` (devices[0] must be the primary's
+ * device; an ordinal may repeat, which puts several members on one GPU -- meant for testing).
+ *   crt_group_commit   = crt_commit for all members: the BVH is built and converted once on the host and the
+ *                        same device layout is uploaded to every GPU in parallel; an instance-only edit
+ *                        re-uploads top-level nodes + instance records only, on every member.
+ *   crt_group_render   = Redraw: the next n_samples sample indices are dealt out in contiguous blocks, member r
+ *                        takes n/N (+1 for r < n mod N); synchronous.  Sample s of pixel p is the same random
+ *                        stream on any GPU, so the members' union is the single-GPU sample set.
+ *   crt_group_read_*   = BufferDump of the combined frame: by default one fused kernel per member reads its
+ *                        block of rows from every member's accumulation buffer over NVLink peer addresses, adds
+ *                        the sums in member order and tone-maps (exchange + Display in one pass, image
+ *                        independent of the member count up to float summation order); with
+ *                        CRT_GROUP_REDUCE=nccl in the environment, or without peer access, ncclReduce to member
+ *                        0 + the ordinary Display pass (libnccl.so.2 is bound with dlopen at group creation).
+ * Setters are called on `primary` only; every crt_group_* call replicates what changed since the last one
+ * (a camera or parameter change restarts the accumulation on all members, as on one context).  Do not call
+ * crt_render / crt_commit on the primary directly while it belongs to a group.  Adaptive screen sampling
+ * is per context and is refused by crt_group_render. */
+typedef struct crt_group crt_group;
+int  crt_group_create(crt_context* primary, const int* devices, int n_devices, crt_group** out_group);
+void crt_group_destroy(crt_group* group);            /* destroys the replicas; `primary` stays with the caller */
+int  crt_group_size(const crt_group* group);
+int  crt_group_member(crt_group* group, int rank, crt_context** out_ctx);   /* for statistics / timing queries */
+int  crt_group_commit(crt_group* group);
+int  crt_group_render(crt_group* group, uint32_t n_samples, uint64_t* out_total_samples);
+int  crt_group_reset_accumulation(crt_group* group, uint64_t first_sample);
+int  crt_group_read_ldr(crt_group* group, uint8_t* rgb8, size_t stride_bytes);
+int  crt_group_read_hdr(crt_group* group, float* rgb32f, size_t stride_bytes);
+/* peer access between all members (1/0), whether the NCCL path is in use, device time (ms, slowest member) of
+ * the exchange + Display kernel of the last crt_group_read_*; any pointer may be NULL */
+int  crt_group_info(crt_group* group, int* out_peer_access, int* out_uses_nccl, double* out_last_reduce_ms);
+
 /* ------------------------------ parity hooks ------------------------------ */
 
 /* Batch SceneNearestHit / SceneAnyHit on caller rays (host arrays of n x 3
@@ -322,6 +360,10 @@ int crt_timing_get(crt_context* ctx, double ms[6], uint64_t launches[6]);
  * triangle vertices, instance records), `total` adds the shading-side arrays (vertex normals, texels, materials,
  * lights, textures, environment).  The bench sizes its L2 / HBM probe with the first. */
 int crt_scene_bytes(crt_context* ctx, size_t* out_traversal, size_t* out_total);
+/* How many crt_commit calls re-uploaded only the top-level nodes and the instance records (an object moved,
+ * changed its material or -- with the number of visible objects unchanged -- its visibility:
+ * ImRaytraceControls.cxx:88, MaterialEditor.cxx:522-523) instead of the whole device layout. */
+int crt_commit_stats(crt_context* ctx, uint64_t* out_top_level_patches);
 /* CUDA stream of the context as an opaque cudaStream_t. */
 int crt_stream(crt_context* ctx, void** out_stream);
 

@@ -92,13 +92,22 @@ struct RenderingParams {
   }
 };
 
-// One render target on one GPU (V3d_View + its OpenGl_View).
+// One render target (V3d_View + its OpenGl_View) on one GPU, or -- constructed with a device list -- on every listed
+// GPU of the box from this one process (crt_group: Update / Redraw / BufferDump go to the group, the rest is set on
+// the view as before and replicated by the library).
 class View {
 public:
   explicit View(int theDevice) { check(crt_create(theDevice, &myCtx)); }
+  explicit View(const std::vector<int>& theDevices)
+  {
+    if (theDevices.empty()) throw Failure(CRT_ERR_INVALID_ARG, "empty device list");
+    check(crt_create(theDevices[0], &myCtx));
+    const int rc = crt_group_create(myCtx, theDevices.data(), (int)theDevices.size(), &myGroup);
+    if (rc != CRT_OK) { Failure f(rc, crt_last_error()); crt_destroy(myCtx); throw f; }
+  }
   struct HostOnly {};
   explicit View(HostOnly) { check(crt_create_host_only(&myCtx)); }
-  ~View() { crt_destroy(myCtx); }
+  ~View() { crt_group_destroy(myGroup); crt_destroy(myCtx); }
   View(const View&) = delete;
   View& operator=(const View&) = delete;
 
@@ -121,12 +130,23 @@ public:
   const RenderingParams& RenderingParameters() const { return myParams; }
   void SetCamera(const crt_camera& c) { myCam = c; myHasCam = true; check(crt_camera_set(myCtx, &c)); }
   void SetWindowSize(uint32_t w, uint32_t h) { check(crt_resize(myCtx, w, h)); myW = w; myH = h; }
-  void Update() { check(crt_commit(myCtx)); }
-  uint64_t Redraw() { uint64_t n = 0; check(crt_render(myCtx, (uint32_t)std::max(1, myParams.SamplesPerPixel), &n)); return n; }
-  uint64_t Redraw(uint32_t samples) { uint64_t n = 0; check(crt_render(myCtx, samples, &n)); return n; }
+  void Update() { check(myGroup ? crt_group_commit(myGroup) : crt_commit(myCtx)); }
+  uint64_t Redraw() { return Redraw((uint32_t)std::max(1, myParams.SamplesPerPixel)); }
+  uint64_t Redraw(uint32_t samples)
+  { uint64_t n = 0; check(myGroup ? crt_group_render(myGroup, samples, &n) : crt_render(myCtx, samples, &n)); return n; }
   // BufferDump(Image_PixMap&, Graphic3d_BT_RGB) returns bool in OCCT (AppGui.cxx:430-433)
-  bool BufferDump(std::vector<uint8_t>& rgb8) { rgb8.resize((size_t)myW * myH * 3); return crt_read_ldr(myCtx, rgb8.data(), 0) == CRT_OK; }
-  bool BufferDumpHdr(std::vector<float>& rgb) { rgb.resize((size_t)myW * myH * 3); return crt_read_hdr(myCtx, rgb.data(), 0) == CRT_OK; }
+  bool BufferDump(std::vector<uint8_t>& rgb8)
+  {
+    rgb8.resize((size_t)myW * myH * 3);
+    return (myGroup ? crt_group_read_ldr(myGroup, rgb8.data(), 0) : crt_read_ldr(myCtx, rgb8.data(), 0)) == CRT_OK;
+  }
+  bool BufferDumpHdr(std::vector<float>& rgb)
+  {
+    rgb.resize((size_t)myW * myH * 3);
+    return (myGroup ? crt_group_read_hdr(myGroup, rgb.data(), 0) : crt_read_hdr(myCtx, rgb.data(), 0)) == CRT_OK;
+  }
+  int Members() const { return myGroup ? crt_group_size(myGroup) : 1; }
+  crt_group* Group() const { return myGroup; }
   // V3d_View::ToPixMap(Image_PixMap&, width, height): off-screen render at the given size (the camera passed in keeps
   // its pose; its aspect is set from the size), `samples` samples per pixel, RGB8 dump.  Returns false like OCCT.
   bool ToPixMap(std::vector<uint8_t>& rgb8, uint32_t w, uint32_t h, crt_camera cam, uint32_t samples)
@@ -139,8 +159,8 @@ public:
     cam.aspect = (float)w / (float)h;
     SetCamera(cam);
     uint64_t n = 0;
-    bool ok = crt_render(myCtx, samples, &n) == CRT_OK;
-    ok = ok && crt_read_ldr(myCtx, (rgb8.resize((size_t)w * h * 3), rgb8.data()), 0) == CRT_OK;
+    bool ok = (myGroup ? crt_group_render(myGroup, samples, &n) : crt_render(myCtx, samples, &n)) == CRT_OK;
+    ok = ok && BufferDump(rgb8);
     if (oldW && oldH && (oldW != w || oldH != h)) SetWindowSize(oldW, oldH);
     if (hadCam) SetCamera(oldCam); else { myHasCam = false; }
     return ok;
@@ -153,6 +173,7 @@ public:
   crt_context* Handle() const { return myCtx; }
 private:
   crt_context* myCtx = nullptr;
+  crt_group* myGroup = nullptr;
   RenderingParams myParams;
   uint32_t myW = 0, myH = 0;
   crt_camera myCam{};

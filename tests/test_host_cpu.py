@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(product_lib):
         assert hasattr(product_lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_ffi.PROTOTYPES), "ctypes prototypes and header disagree"
     version = int(re.search(r"#define CRT_ABI_VERSION (\d+)", header).group(1))
-    assert product_lib.crt_abi_version() == version == 2
+    assert product_lib.crt_abi_version() == version == 3
 
 
 def test_struct_layouts_match_header():
@@ -58,8 +58,9 @@ def test_no_device_fails_loudly(product_lib):
 
 
 def test_product_never_imports_the_oracle():
-    """No include, import, link or dlopen of anything under oracle/ from the product tree."""
-    bad = re.compile(r"(#\s*include[^\n]*oracle|^\s*(from|import)\s+oracle|oracle_ffi|libcadrays_oracle|dlopen)", re.M)
+    """No include, import, link or dlopen of anything under oracle/ from the product tree (the one dlopen the
+    product makes is NCCL's own library, for crt_group's optional ncclReduce path)."""
+    bad = re.compile(r"(#\s*include[^\n]*oracle|^\s*(from|import)\s+oracle|oracle_ffi|libcadrays_oracle|dlopen\s*\((?!\"libnccl\.so\.2\"))", re.M)
     files = list((REPO / "cadrays_b200").rglob("*.py")) + [p for p in (REPO / "cadrays_b200" / "csrc").glob("*") if p.is_file()]
     files.append(REPO / "include" / "cadrays_b200.h")
     files.append(REPO / "include" / "cadrays_b200.hpp")
