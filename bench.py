@@ -420,6 +420,9 @@ def run_ours(args):
     rank, local, world = D.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world
+    # host-side barrier (gloo): an NCCL barrier keeps a kernel spinning on the GPUs of the ranks that wait, and the
+    # group e2e below has rank 0 render on every GPU while the other ranks wait
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
@@ -554,6 +557,54 @@ def run_ours(args):
     view.Remove()
     del accum, reduced
     torch.cuda.empty_cache()
+
+    # ---- e2e through the call a single-process host makes (crt_group behind V3d_View: AppViewer.cxx:1047 Redraw,
+    # :1259-1262 BufferDump): rank 0 alone drives all N GPUs -- scene built once on the host and uploaded to every
+    # GPU, the step's samples dealt out over the GPUs, the partial sums exchanged over NVLink peer memory and
+    # tone-mapped by the fused kernel, ONE combined RGB8 frame in a pinned host buffer.  The other ranks' GPUs are idle
+    # (their contexts are gone) and their processes wait on a host-side barrier.
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                gv = V3d_View(devices=list(range(world)))
+                tg0 = time.perf_counter()
+                desc.apply(gv)
+                t_group_commit = time.perf_counter() - tg0
+                p = desc.params
+                p.SamplesPerBatch = B
+                gv.SetRenderingParams(p)
+                gv.Update()
+
+                def group_run(spp_total, n_steps):
+                    for _ in range(2):
+                        gv.SetCamera(cam); gv.Redraw(spp_total); gv.BufferDump(Graphic3d_BT_RGB, ldr)
+                    t0 = time.perf_counter()
+                    for _ in range(n_steps):
+                        gv.SetCamera(cam)                         # restarts the accumulation on every GPU
+                        gv.Redraw(spp_total)                      # one call, N GPUs
+                        gv.BufferDump(Graphic3d_BT_RGB, ldr)      # exchange + Display + device -> host
+                    return time.perf_counter() - t0
+                dtw = group_run(B * world, e2e_steps)
+                dts = group_run(B, e2e_steps)
+                info = gv.GroupInfo()
+                line["e2e_ranks"] = line["e2e"]
+                line["e2e"] = {
+                    "value": W * H * B * world * e2e_steps / dtw / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * B * world + 64 * world,
+                    "d2h_bytes_per_step": W * H * 3, "steps": e2e_steps, "scaling": "weak",
+                    "call": "ONE host process, crt_group over all N GPUs: SetCamera + Redraw(spp x N) + BufferDump(RGB8) per step "
+                            "(samples dealt out over the GPUs, partial sums read over NVLink peer memory by the fused reduce + Display "
+                            "kernel, one combined frame in a pinned host buffer); wall clock",
+                    "exchange": "nccl" if info["nccl"] else "fused peer-memory kernel", "exchange_display_ms": info["reduce_ms"],
+                    "group_commit_s": t_group_commit,
+                    "strong": {"scaling": "strong", "spp_per_step_total": B, "value": W * H * B * e2e_steps / dts / 1e6, "unit": UNIT,
+                               "ms_per_step": dts / e2e_steps * 1e3},
+                }
+                gv.Remove()
+            except Exception as ex:                      # the per-rank e2e above stays the reported number
+                line["e2e_group_error"] = repr(ex)
+        dist.barrier(group=host_group)
 
     # ---- second block: the HBM-resident case, config C5 flattened (10.5 M unique triangles, 1.3 GB of scene data)
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "assembly":

@@ -58,7 +58,7 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
-constexpr size_t kCounterWords = 4 * 64 + 8;   // queue lengths and work counters of one (half-)wave
+constexpr size_t kCounterWords = 4 * 64 + 8;   // queue lengths and work counters of one wave part
 
 enum Family { F_GENERATE = 0, F_EXTEND, F_SHADE, F_CONNECT, F_RESOLVE, F_RENDER, F_COUNT };
 
@@ -146,10 +146,24 @@ struct crt_context {
   int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
                                 // 18.90 / 18.80 / 18.57 / 18.45 / 18.43 / 18.47 ms of traversal per step)
   bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
-  bool pipeline = false;
-  int pipeline_trace_ctas = 5;
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // per-path kernel for the thin end of a wave (k_tail): from bounce `tail_min_depth` on, once at most `tail_max` paths
+  // are active, one launch carries them to their end (CRT_TAIL=0 disables, CRT_TAIL_MAX / CRT_TAIL_MIN_DEPTH tune)
+  bool tail = true;
+  uint32_t tail_max = 0;        // 0 = one path per resident thread of k_tail (set in crt_create)
+  int tail_min_depth = 1;
+  // a wave split into `parts` ranges of 8x4 pixel tiles, each on its own stream: every launch of a thin wave ends
+  // with a tail in which a few long rays finish while most SMs idle, and the parts fill each other's tails.
+  // pipeline: 0 = never, 1 = always, 2 = automatic (waves of at most pipeline_auto_paths paths: the reference's
+  // cadence of one sample per Redraw).  CRT_PIPELINE / CRT_PIPELINE_PARTS / CRT_PIPELINE_AUTO_PATHS.
+  int pipeline = 2;
+  int pipeline_parts = 2;
+  uint64_t pipeline_auto_paths = 5ull << 20;
+  int pipeline_trace_ctas = 0;   // cap of the traversal grids (CTAs per SM) while split; 0 = none
+  static constexpr int kMaxParts = 4;
+  cudaStream_t side_stream[kMaxParts - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts - 1] = {};
+  struct WavePart { size_t slot0; int index; };
+  std::vector<WavePart> last_parts;   // how the last wave was laid out (crt_wavefront_rays)
 
   // metrics
   DevBuf<Counters> d_counters;
@@ -249,6 +263,8 @@ void update_device_params(crt_context* c)
   P.width = c->width; P.height = c->height;
   P.tiles_x = (c->width + 7u) / 8u;
   P.tiles_y = (c->height + 3u) / 4u;
+  P.tile0 = 0;
+  P.n_tiles = P.tiles_x * P.tiles_y;
 }
 
 int ensure_path_slots(crt_context* c, uint64_t need)
@@ -518,10 +534,10 @@ PathState make_state(crt_context* c, size_t slot0, int half)
 
 // generate + all bounces of one (half-)wave on stream s; path state indices are relative to st
 template <bool COUNT, bool QUAD>
-int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_t n_batch, const uint32_t* d_seeds,
+int enqueue_bounces(crt_context* c, const PathState& st, const DeviceParams& dp, cudaStream_t s, uint32_t n_batch, const uint32_t* d_seeds,
                     const AdaptiveState* adaptive, int trace_ctas)
 {
-  const int depth_max = c->dp.max_depth;
+  const int depth_max = dp.max_depth;
   Counters* gc = c->d_counters.p;
   const bool pers = c->persistent || QUAD;      // the 4-wide walk exists in the persistent driver only
   const bool fuse = pers && c->fuse_traversal;
@@ -537,16 +553,16 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
   const int r_pri = c->sm_count * p_pri;
   if (!primary) {
     SpanGuard g(c, F_GENERATE, s);
-    if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, *adaptive, d_seeds, n_batch);
-    else k_generate<<<grid_for(c, 8), 256, 0, s>>>(st, c->dp, d_seeds, n_batch);
+    if (adaptive) k_generate_adaptive<<<grid_for(c, 8), 256, 0, s>>>(st, dp, *adaptive, d_seeds, n_batch);
+    else k_generate<<<grid_for(c, 8), 256, 0, s>>>(st, dp, d_seeds, n_batch);
   }
   for (int depth = 0; depth < depth_max; ++depth) {
     // closest hits of this bounce; when fused, the same launch also resolves the previous bounce's shadow rays
     {
       SpanGuard g(c, F_EXTEND, s);
       if (primary && depth == 0 && !QUAD && c->primary_lockstep)
-        k_extend_primary_lockstep<COUNT><<<grid_for(c, c->primary_grid), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
-      else if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, c->dp, d_seeds, n_batch, gc);
+        k_extend_primary_lockstep<COUNT><<<grid_for(c, c->primary_grid), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, dp, d_seeds, n_batch, gc);
+      else if (primary && depth == 0) k_extend_primary<COUNT, QUAD><<<std::min(r_pri, cap), CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, dp, d_seeds, n_batch, gc);
       else if (fuse && depth > 0) k_trace_dual<COUNT, QUAD><<<g_dual, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       else if (pers && !(depth == 0 && !QUAD && c->primary_lockstep)) k_extend<COUNT, true, QUAD><<<g_ext, CRT_TRACE_BLOCK, 0, s>>>(c->ds, st, depth, gc);
       // camera rays that went through a generate pass (adaptive sampling, ragged sizes): lockstep as well
@@ -555,8 +571,16 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
     {
       SpanGuard g(c, F_SHADE, s);
       const dim3 sg(grid_for(c, 8));
-#define CRT_SHADE(TEXV, FIRSTV, SORTV, LEANV) k_shade<COUNT, TEXV, FIRSTV, SORTV, LEANV><<<sg, 128, 0, s>>>(c->ds, c->dp, st, depth, gc, d_seeds)
       const bool lean = c->mats_lean && !c->ds.n_tex;
+      // the thin end of the wave: k_tail finishes the paths of this bounce when few are left, k_shade then skips them
+      const uint32_t tail_max = (c->tail && !QUAD && depth >= std::max(1, c->tail_min_depth)) ? c->tail_max : 0u;   // k_tail walks the binary layout
+      if (tail_max) {
+        const int tg = c->sm_count * CRT_TAIL_MIN_BLOCKS;
+        if (c->ds.n_tex) k_tail<COUNT, true, false><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
+        else if (lean) k_tail<COUNT, false, true><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
+        else k_tail<COUNT, false, false><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
+      }
+#define CRT_SHADE(TEXV, FIRSTV, SORTV, LEANV) k_shade<COUNT, TEXV, FIRSTV, SORTV, LEANV><<<sg, 128, 0, s>>>(c->ds, dp, st, depth, gc, d_seeds, tail_max)
       if (primary && depth == 0) {
         if (c->ds.n_tex) CRT_SHADE(true, true, false, false); else if (lean) CRT_SHADE(false, true, false, true); else CRT_SHADE(false, true, false, false);
       } else if (c->shade_sort && depth > 0) {
@@ -576,35 +600,49 @@ int enqueue_bounces(crt_context* c, const PathState& st, cudaStream_t s, uint32_
 }
 
 // One wave: n_batch samples of every pixel, or (adaptive != nullptr) `n_batch` tile samples dealt out by
-// k_adaptive_allocate.  Pipelined form: the wave is split into two half-waves that run on two streams, so the
-// shading kernels of one half (latency / HBM bound) share the SMs with the traversal kernels of the other
-// (L1 / ALU bound); the halves are accumulated in sample order, so the result does not change.
+// k_adaptive_allocate.  Split form: the frame's 8x4 pixel tiles are divided into `parts` ranges; every part is a
+// complete small wave (its own path-state slots, queues and counters, its own k_resolve over its own pixels) on its own
+// stream, so the latency-bound end of one part's launches overlaps the other parts' work.  Per-path results do not
+// depend on the split (a path's stream is a function of its pixel and sample index only).
 template <bool COUNT, bool QUAD>
 int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, const AdaptiveState* adaptive = nullptr)
 {
   const int depth_max = c->dp.max_depth;
   Counters* gc = c->d_counters.p;
-  const bool split = c->pipeline && !adaptive && n_batch >= 2 && c->stream2;
-  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * ((split ? kCounterWords : 0) + 4 * depth_max + 2), c->stream));
-  if (!split) {
+  const uint32_t n_tiles = c->dp.tiles_x * c->dp.tiles_y;
+  const uint64_t paths = (uint64_t)n_tiles * 32u * n_batch;
+  int parts = 1;
+  if (!adaptive && c->side_stream[0] && (c->pipeline == 1 || (c->pipeline == 2 && paths <= c->pipeline_auto_paths)))
+    parts = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(c->pipeline_parts, (int)crt_context::kMaxParts)), std::max(1u, n_tiles / 64u));
+  CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * ((size_t)(parts - 1) * kCounterWords + 4 * depth_max + 2), c->stream));
+  c->last_parts.clear();
+  if (parts == 1) {
     const PathState st = make_state(c, 0, 0);
-    enqueue_bounces<COUNT, QUAD>(c, st, c->stream, n_batch, d_seeds, adaptive, 0);
+    c->last_parts.push_back({ 0, 0 });
+    enqueue_bounces<COUNT, QUAD>(c, st, c->dp, c->stream, n_batch, d_seeds, adaptive, 0);
     SpanGuard g(c, F_RESOLVE);
     if (adaptive) k_resolve_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, c->accum, COUNT ? gc : nullptr);
     else k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
   } else {
-    const uint32_t n_a = (n_batch + 1) / 2, n_b = n_batch - n_a;
-    const size_t per_sample = (size_t)c->dp.tiles_x * c->dp.tiles_y * 32u;
-    const PathState st_a = make_state(c, 0, 0), st_b = make_state(c, per_sample * n_a, 1);
     CRT_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-    CRT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    enqueue_bounces<COUNT, QUAD>(c, st_a, c->stream, n_a, d_seeds, nullptr, c->pipeline_trace_ctas);
-    enqueue_bounces<COUNT, QUAD>(c, st_b, c->stream2, n_b, d_seeds + n_a, nullptr, c->pipeline_trace_ctas);
-    CRT_CUDA(cudaEventRecord(c->ev_join, c->stream2));
-    SpanGuard g(c, F_RESOLVE);
-    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st_a, c->dp, c->accum, n_a, COUNT ? gc : nullptr);
-    CRT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st_b, c->dp, c->accum, n_b, COUNT ? gc : nullptr);
+    size_t slot0 = 0;
+    for (int k = 0; k < parts; ++k) {
+      cudaStream_t s = k == 0 ? c->stream : c->side_stream[k - 1];
+      DeviceParams dp = c->dp;
+      dp.tile0 = (uint32_t)((uint64_t)n_tiles * k / parts);
+      dp.n_tiles = (uint32_t)((uint64_t)n_tiles * (k + 1) / parts) - dp.tile0;
+      const PathState st = make_state(c, slot0, k);
+      c->last_parts.push_back({ slot0, k });
+      if (k > 0) CRT_CUDA(cudaStreamWaitEvent(s, c->ev_fork, 0));
+      enqueue_bounces<COUNT, QUAD>(c, st, dp, s, n_batch, d_seeds, nullptr, c->pipeline_trace_ctas);
+      {
+        SpanGuard g(c, F_RESOLVE, s);
+        k_resolve<<<grid_for(c, 4), 256, 0, s>>>(st, dp, c->accum, n_batch, COUNT ? gc : nullptr);   // the parts own disjoint pixels
+      }
+      if (k > 0) CRT_CUDA(cudaEventRecord(c->ev_join[k - 1], s));
+      slot0 += (size_t)dp.n_tiles * 32u * n_batch;
+    }
+    for (int k = 1; k < parts; ++k) CRT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[k - 1], 0));
   }
   CRT_CUDA(cudaGetLastError());
   return CRT_OK;
@@ -676,7 +714,7 @@ int render_impl(crt_context* c, uint32_t n_samples)
   if ((rc = upload_tables(c))) return rc;
   update_device_params(c);
   if (n_samples == 0) return CRT_OK;
-  CRT_CUDA(c->counters.ensure(2 * kCounterWords));
+  CRT_CUDA(c->counters.ensure(crt_context::kMaxParts * kCounterWords));
   if (c->params.adaptive_sampling) return render_adaptive(c, n_samples);
   const uint32_t batch = std::min(auto_batch(c), n_samples);
   if ((rc = ensure_path_state(c, batch))) return rc;
@@ -763,17 +801,25 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_PRIMARY_LOCKSTEP")) c->primary_lockstep = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_GRID")) c->primary_grid = std::max(1, std::atoi(tv));
   if (const char* tv = std::getenv("CRT_FUSE_PRIMARY")) c->fuse_primary = std::atoi(tv) != 0;
-  if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::atoi(tv) != 0;
-  if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(1, std::atoi(tv));
+  if (const char* tv = std::getenv("CRT_TAIL")) c->tail = std::atoi(tv) != 0;
+  c->tail_max = (uint32_t)c->sm_count * CRT_TAIL_MIN_BLOCKS * 128u;
+  if (const char* tv = std::getenv("CRT_TAIL_MAX")) c->tail_max = (uint32_t)std::max(0, std::atoi(tv));
+  if (const char* tv = std::getenv("CRT_TAIL_MIN_DEPTH")) c->tail_min_depth = std::max(1, std::atoi(tv));
+  if (const char* tv = std::getenv("CRT_PIPELINE")) c->pipeline = std::max(0, std::min(2, std::atoi(tv)));
+  if (const char* tv = std::getenv("CRT_PIPELINE_PARTS")) c->pipeline_parts = std::max(1, std::min((int)crt_context::kMaxParts, std::atoi(tv)));
+  if (const char* tv = std::getenv("CRT_PIPELINE_AUTO_PATHS")) c->pipeline_auto_paths = (uint64_t)std::max(0ll, std::atoll(tv));
+  if (const char* tv = std::getenv("CRT_PIPELINE_TRACE_CTAS")) c->pipeline_trace_ctas = std::max(0, std::atoi(tv));
 
   crt_params_default(&c->params);
   std::memset(&c->cam, 0, sizeof c->cam);
   c->cam.dir[1] = 1.0f; c->cam.up[2] = 1.0f; c->cam.fovy_deg = 45.0f; c->cam.aspect = 1.0f; c->cam.ortho_scale = 1.0f;
   cudaError_t se = cudaSetDevice(device_ordinal);
   if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  for (int k = 0; k < crt_context::kMaxParts - 1; ++k) {
+    if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->side_stream[k], cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming);
+  }
   if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-  if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (se == cudaSuccess) se = c->d_counters.ensure(1);
   if (se == cudaSuccess) se = cudaMemset(c->d_counters.p, 0, sizeof(Counters));
   if (se != cudaSuccess) {
@@ -813,8 +859,10 @@ void crt_destroy(crt_context* c)
   c->accum_internal.release(); c->d_ldr.release(); c->d_hdr.release(); c->d_counters.release();
   c->ad_count.release(); c->ad_err.release(); c->ad_cum.release(); c->ad_qoff.release(); c->ad_seeds.release(); c->ad_even.release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
+  for (int k = 0; k < crt_context::kMaxParts - 1; ++k) {
+    if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    if (c->side_stream[k]) cudaStreamDestroy(c->side_stream[k]);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1293,32 +1341,44 @@ int crt_wavefront_rays(crt_context* c, int depth, int kind, float* org, float* d
   if (!c->state_capacity || !c->counters.p) return fail(CRT_ERR_STATE, "crt_wavefront_rays before crt_render");
   CRT_REQUIRE(depth >= 0 && depth < c->dp.max_depth, "depth outside the last wave");
   CRT_REQUIRE(kind == 1 || depth >= 1, "camera rays are not stored (they are recomputed from the pixel and the frame seed)");
-  if (c->pipeline) return fail(CRT_ERR_STATE, "crt_wavefront_rays: not available with CRT_PIPELINE=1");
   if (c->params.adaptive_sampling) return fail(CRT_ERR_STATE, "crt_wavefront_rays: not available with adaptive sampling");
+  if (c->last_parts.empty()) return fail(CRT_ERR_STATE, "crt_wavefront_rays before crt_render");
   CRT_CUDA(cudaStreamSynchronize(c->stream));
-  const PathState st = make_state(c, 0, 0);
-  uint32_t n = 0;
-  CRT_CUDA(cudaMemcpy(&n, (kind ? st.n_shadow : st.n_active) + depth, sizeof n, cudaMemcpyDeviceToHost));
-  *out_n = n;
-  const uint32_t m = std::min(n, capacity);
-  if (m == 0 || (!org && !dir && !tmax)) return CRT_OK;
-  DevBuf<float4> d_o, d_d;
-  cudaError_t e = d_o.ensure(m);
-  if (e == cudaSuccess) e = d_d.ensure(m);
-  std::vector<float4> ho(m), hd(m);
-  if (e == cudaSuccess) {
-    k_gather_rays<<<grid_for(c, 8), 256, 0, c->stream>>>(st, st.queue[depth & 1], m, kind, d_o.p, d_d.p);
-    e = cudaGetLastError();
+  // a wave may have been split into parts (tile ranges on several streams): their rays are returned part after part
+  std::vector<uint32_t> counts(c->last_parts.size(), 0);
+  uint64_t total = 0;
+  for (size_t k = 0; k < c->last_parts.size(); ++k) {
+    const PathState st = make_state(c, c->last_parts[k].slot0, c->last_parts[k].index);
+    CRT_CUDA(cudaMemcpy(&counts[k], (kind ? st.n_shadow : st.n_active) + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    total += counts[k];
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ho.data(), d_o.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(hd.data(), d_d.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  d_o.release(); d_d.release();
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? CRT_ERR_OUT_OF_MEMORY : CRT_ERR_CUDA, cudaGetErrorString(e)); }
-  for (uint32_t i = 0; i < m; ++i) {
-    if (org) { org[3 * (size_t)i] = ho[i].x; org[3 * (size_t)i + 1] = ho[i].y; org[3 * (size_t)i + 2] = ho[i].z; }
-    if (dir) { dir[3 * (size_t)i] = hd[i].x; dir[3 * (size_t)i + 1] = hd[i].y; dir[3 * (size_t)i + 2] = hd[i].z; }
-    if (tmax) tmax[i] = hd[i].w;
+  *out_n = (uint32_t)std::min<uint64_t>(total, 0xffffffffull);
+  if (total == 0 || capacity == 0 || (!org && !dir && !tmax)) return CRT_OK;
+  uint32_t written = 0;
+  for (size_t k = 0; k < c->last_parts.size() && written < capacity; ++k) {
+    const uint32_t m = std::min(counts[k], capacity - written);
+    if (m == 0) continue;
+    const PathState st = make_state(c, c->last_parts[k].slot0, c->last_parts[k].index);
+    DevBuf<float4> d_o, d_d;
+    cudaError_t e = d_o.ensure(m);
+    if (e == cudaSuccess) e = d_d.ensure(m);
+    std::vector<float4> ho(m), hd(m);
+    if (e == cudaSuccess) {
+      k_gather_rays<<<grid_for(c, 8), 256, 0, c->stream>>>(st, st.queue[depth & 1], m, kind, d_o.p, d_d.p);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ho.data(), d_o.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hd.data(), d_d.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d_o.release(); d_d.release();
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? CRT_ERR_OUT_OF_MEMORY : CRT_ERR_CUDA, cudaGetErrorString(e)); }
+    for (uint32_t i = 0; i < m; ++i) {
+      const size_t o = (size_t)written + i;
+      if (org) { org[3 * o] = ho[i].x; org[3 * o + 1] = ho[i].y; org[3 * o + 2] = ho[i].z; }
+      if (dir) { dir[3 * o] = hd[i].x; dir[3 * o + 1] = hd[i].y; dir[3 * o + 2] = hd[i].z; }
+      if (tmax) tmax[o] = hd[i].w;
+    }
+    written += m;
   }
   return CRT_OK;
 }

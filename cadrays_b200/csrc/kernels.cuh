@@ -66,6 +66,9 @@ struct DeviceParams {
   int32_t is_ortho;
   uint32_t width, height;
   uint32_t tiles_x, tiles_y;    // 8x4 pixel tiles per warp
+  // the part of the frame this launch works on: 8x4 tiles [tile0, tile0 + n_tiles) in row-major tile order (the whole
+  // frame unless a wave is split into parts that run on several streams); path slot = sample * n_tiles * 32 + tile * 32 + lane
+  uint32_t tile0, n_tiles;
 };
 
 struct Counters {   // mirrors crt_stats
@@ -971,7 +974,7 @@ __device__ __forceinline__ void generate_path(const PathState& st, const DeviceP
 __global__ void __launch_bounds__(256)
 k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seeds, uint32_t n_batch)
 {
-  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t per_sample = P.n_tiles * 32u;
   const uint32_t total = per_sample * n_batch;
   const uint32_t stride = gridDim.x * blockDim.x;
   const bool aligned = (P.width & 7u) == 0 && (P.height & 3u) == 0;
@@ -979,7 +982,7 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
     const uint32_t slot = base + (threadIdx.x & 31u);
     const uint32_t k = slot / per_sample;
     const uint32_t in = slot - k * per_sample;
-    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
     const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
     const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
     const bool valid = slot < total && px < P.width && py < P.height;
@@ -1049,7 +1052,7 @@ struct PrimaryPolicy {
   __device__ __forceinline__ uint32_t load(uint32_t slot, v3& o, v3& d, float& tmax, bool&) const
   {
     const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
     uint32_t rng;
     camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
     tmax = CRT_MAXFLOAT;
@@ -1066,7 +1069,7 @@ template <bool COUNT, bool QUAD>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __restrict__ seeds, uint32_t n_batch, Counters* gcnt)
 {
-  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t per_sample = P.n_tiles * 32u;
   const uint32_t n = per_sample * n_batch;
   Counters cnt = {};
   PrimaryPolicy pol{ st, P, seeds, per_sample };
@@ -1082,12 +1085,12 @@ template <bool COUNT>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __restrict__ seeds, uint32_t n_batch, Counters* gcnt)
 {
-  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t per_sample = P.n_tiles * 32u;
   const uint32_t n = per_sample * n_batch;
   Counters cnt = {};
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
     const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
     v3 o, d;
     uint32_t rng;
     camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
@@ -1099,6 +1102,145 @@ k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uin
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = n;
   if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// One bounce of PathTrace for one path whose closest hit is `hh` (t, u, v, triangle slot):
+// implicit light / environment hit with MIS, emission, next-event estimation (fills the shadow ray), Beer-Lambert
+// absorption, layered-BSDF sampling, termination / Russian roulette, continuation ray.  Shared by the wavefront
+// kernel k_shade and by the per-path kernel k_tail, so both run the same arithmetic in the same order.
+// The instance id of the hit is read from *inst_src when given (wavefront: st.hit_inst), else it is inst_reg.
+template <bool COUNT, bool TEX, bool LEAN>
+__device__ __forceinline__ void shade_bounce(const DeviceScene& S, const DeviceParams& P, const int depth, const bool two_sided,
+                                             const float eps, const float4 hh, const int32_t* inst_src, const int32_t inst_reg,
+                                             v3& org, v3& dir, v3& thr, float& imp_pdf, uint32_t& rng, bool& inside, v3& radiance,
+                                             bool& want_shadow, v3& sh_o, v3& sh_d, v3& sh_c, float& sh_tmax, bool& want_next,
+                                             Counters& cnt)
+{
+  const int32_t tri = __float_as_int(hh.w);
+  const bool found = tri >= 0;
+
+  float exp_pdf;
+  const v3 le = intersect_light(S, P, org, dir, depth, hh.x, exp_pdf);
+  if (any_gt(le, 0.0f) || !found) {
+    const float mis = (depth == 0 || imp_pdf == CRT_MAXFLOAT) ? 1.0f
+                    : imp_pdf * imp_pdf / (exp_pdf * exp_pdf + imp_pdf * imp_pdf);
+    radiance = vadd(radiance, vscale(vmul(thr, le), mis));
+  } else {
+    const int32_t inst = inst_src ? ld_stream(inst_src) : inst_reg;
+    const float4* ir = S.inst + 4 * (size_t)inst;
+    float4 m0, m1, m2, m3;
+    ld_record64(ir, m0, m1, m2, m3);
+    const v3 c0 = V(m0.x, m1.x, m2.x), c1 = V(m0.y, m1.y, m2.y), c2 = V(m0.z, m1.z, m2.z);
+    // geometric normal from the stored vertices (same expression as tri_test's nn)
+    const float4* tv = S.tri_verts + kTriStride * (size_t)tri;
+    float4 a, b, c;
+    ld_triangle(tv, a, b, c);
+    const v3 p0 = V(a.x, a.y, a.z), p1 = V(b.x, b.y, b.z), p2 = V(c.x, c.y, c.z);
+    const v3 nraw = cross3(vsub(p0, p2), vsub(p1, p0));
+    const v3 ng = normalize3(V(dot3(c0, nraw), dot3(c1, nraw), dot3(c2, nraw)));
+    org = vadd(org, vscale(dir, hh.x));
+    // SmoothNormal, SURVEY A.4
+    const float4* tn = S.tri_nrm + 3 * (size_t)tri;
+    const v3 n0 = ld_rgb(tn, 0), n1 = ld_rgb(tn, 1), n2 = ld_rgb(tn, 2);
+    v3 ns = vadd(vadd(vscale(n1, hh.y), vscale(n2, hh.z)), vscale(n0, (1.0f - hh.y) - hh.z));
+    ns = normalize3(ns);
+    ns = normalize3(V(dot3(c0, ns), dot3(c1, ns), dot3(c2, ns)));
+    const Frame frame = build_frame(ns);
+
+    const uint32_t mat_id = (uint32_t)__float_as_int(m3.y);
+    Bsdf B;
+    v3 mat_le, absorp;
+    float absorp_k, kd_w = 0.0f, kt_w = 0.0f, le_w = 0.0f;   // texture id + 1, S scale, T scale
+    if (mat_id < S.n_mats) {
+      const float4* mp = S.mats + 8 * (size_t)mat_id;
+      const float4 kc = __ldg(mp), kd = __ldg(mp + 1), ks = __ldg(mp + 2), kt = __ldg(mp + 3);
+      const float4 le4 = __ldg(mp + 4), fc = __ldg(mp + 5), fb = __ldg(mp + 6), ab = __ldg(mp + 7);
+      B.Kc = V(kc.x, kc.y, kc.z); B.Kc_w = kc.w;
+      B.Kd = V(kd.x, kd.y, kd.z);
+      B.Ks = V(ks.x, ks.y, ks.z); B.Ks_w = ks.w;
+      B.Kt = V(kt.x, kt.y, kt.z);
+      B.Fc = V(fc.x, fc.y, fc.z); B.Fb = V(fb.x, fb.y, fb.z);
+      mat_le = V(le4.x, le4.y, le4.z);
+      absorp = V(ab.x, ab.y, ab.z); absorp_k = ab.w;
+      kd_w = kd.w; kt_w = kt.w; le_w = le4.w;
+    } else {   // default grey diffuse (same record as the oracle's k_default_bsdf)
+      B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kd = V(0.8f, 0.8f, 0.8f); B.Ks = V(0, 0, 0); B.Ks_w = 0.0f;
+      B.Kt = V(0, 0, 0); B.Fc = V(-1.0f, 0.0f, 0.0f); B.Fb = V(-1.0f, 0.0f, 1.0f);
+      mat_le = V(0, 0, 0); absorp = V(0, 0, 0); absorp_k = 0.0f;
+    }
+    if (COUNT) cnt.shaded_hits++;
+
+    // base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV)
+    if (TEX) {   // instantiated only for scenes that have textures
+      if (kd_w >= 1.0f && (uint32_t)kd_w - 1u < S.n_tex) {
+        const float2* tu = S.tri_uv + 3 * (size_t)tri;
+        const float2 uv0 = __ldg(tu), uv1 = __ldg(tu + 1), uv2 = __ldg(tu + 2);
+        const float w0 = (1.0f - hh.y) - hh.z;
+        const float su = (uv1.x * hh.y + uv2.x * hh.z) + uv0.x * w0;
+        const float sv = (uv1.y * hh.y + uv2.y * hh.z) + uv0.y * w0;
+        const float ss = kt_w != 0.0f ? kt_w : 1.0f, ts = le_w != 0.0f ? le_w : 1.0f;
+        const float4 tc = tex_lookup(S, (uint32_t)kd_w - 1u, su * ss, sv * ts);
+        B.Kd = vmul(B.Kd, vscale(V(tc.x * tc.x, tc.y * tc.y, tc.z * tc.z), tc.w));
+        if (tc.w != 1.0f) {
+          const float ia = 1.0f - tc.w;
+          B.Kt = V(ia + tc.w * B.Kt.x, ia + tc.w * B.Kt.y, ia + tc.w * B.Kt.z);
+        }
+      }
+    }
+
+    const v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), frame);
+    if (LEAN) {   // host guarantee: no coat, no transmission anywhere in the material table (and so never inside a medium)
+      B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kt = V(0, 0, 0);
+      inside = false;
+    }
+    radiance = vadd(radiance, vmul(thr, mat_le));
+
+    const v3 nee_k = vadd(B.Kd, vadd(B.Ks_w > CRT_FLT_EPS ? B.Ks : V(0, 0, 0), B.Kc_w > CRT_FLT_EPS ? B.Kc : V(0, 0, 0)));
+    if (S.n_lights > 0 && dot3(nee_k, thr) > 0.0f) {
+      exp_pdf = 1.0f / (float)S.n_lights;
+      int li = (int)(rand_float(rng) * (float)S.n_lights);
+      if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+      const float4 le_w = __ldg(S.lights + 2 * li), lp = __ldg(S.lights + 2 * li + 1);
+      const bool infinite = lp.w == 0.0f;
+      const v3 to = infinite ? V(lp.x, lp.y, lp.z) : vsub(V(lp.x, lp.y, lp.z), org);
+      const float dist = sqrtf(dot3(to, to));
+      const v3 ldir = sample_light(to, dist, infinite, le_w.w, exp_pdf, rng);
+      const v3 wl = to_local(ldir, frame);
+      const float bpdf = bsdf_pdf_layered(B, wo, wl, thr);
+      imp_pdf = bpdf;
+      const float mis = (exp_pdf == CRT_MAXFLOAT) ? 1.0f : exp_pdf / (exp_pdf * exp_pdf + bpdf * bpdf);
+      const v3 contrib = vscale(vmul(V(le_w.x, le_w.y, le_w.z), eval_bsdf_layered(B, wl, wo, two_sided)), mis);
+      if (any_gt(contrib, CRT_MIN_CONTRIBUTION)) {
+        const float side = dot3(ng, ldir) >= 0.0f ? eps : -eps;
+        sh_o = vadd(vadd(org, vscale(ldir, eps)), vscale(ng, side));
+        sh_d = ldir;
+        sh_tmax = infinite ? CRT_MAXFLOAT : dist;
+        sh_c = vmul(thr, contrib);
+        want_shadow = true;
+      }
+    }
+
+    if (inside) {
+      thr = vmul(thr, V(exp_poly(-hh.x * absorp_k * (1.0f - absorp.x)),
+                        exp_poly(-hh.x * absorp_k * (1.0f - absorp.y)),
+                        exp_poly(-hh.x * absorp_k * (1.0f - absorp.z))));
+    }
+
+    v3 wi;
+    imp_pdf = sample_bsdf_layered<LEAN>(B, wo, wi, thr, inside, rng, two_sided);
+
+    float survive = any_gt(thr, CRT_MIN_THROUGHPUT) ? 1.0f : 0.0f;
+    const bool rr_on = P.russian_roulette && depth >= 3;
+    if (rr_on) survive = minf(fmaf(0.0722f, thr.z, fmaf(0.7152f, thr.y, 0.2126f * thr.x)), 0.95f);
+    const bool dead = rand_float(rng) > survive || all_lt(thr, CRT_MIN_THROUGHPUT);
+    if (!dead && depth + 1 < P.max_depth) {
+      if (rr_on) thr = vscale(thr, 1.0f / survive);
+      dir = normalize3(from_local(wi, frame));
+      const float side = dot3(ng, dir) >= 0.0f ? eps : -eps;
+      org = vadd(vadd(org, vscale(dir, eps)), vscale(ng, side));
+      want_next = true;
+    }
+  }
 }
 
 // One bounce of PathTrace for every active path: implicit
@@ -1117,9 +1259,10 @@ k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uin
 constexpr uint32_t kShadeBatch = CRT_SHADE_BATCH;
 template <bool COUNT, bool TEX, bool FIRST, bool SORT, bool LEAN>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
-k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds)
+k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds, uint32_t tail_max)
 {
   const uint32_t n = st.n_active[depth];
+  if (!FIRST && n <= tail_max) return;     // k_tail(depth) has carried these paths to their end (same test there)
   const uint32_t* __restrict__ q = st.queue[depth & 1];
   uint32_t* __restrict__ qn = st.queue[(depth + 1) & 1];
   Counters cnt = {};
@@ -1177,9 +1320,9 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
       if (FIRST) {
         // depth 0 after k_extend_primary: slot i is pixel sample i; its state is (camera ray, throughput 1, radiance 0)
         slot = i;
-        const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+        const uint32_t per_sample = P.n_tiles * 32u;
         const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-        const uint32_t tile = in >> 5, ln = in & 31u;
+        const uint32_t tile = P.tile0 + (in >> 5), ln = in & 31u;
         camera_ray(P, (tile % P.tiles_x) * 8u + (ln & 7u), (tile / P.tiles_x) * 4u + (ln >> 3), __ldg(seeds + k), org, dir, rng);
         thr = V(1.0f, 1.0f, 1.0f);
         rr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1195,132 +1338,9 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
         thr = V(tw.x, tw.y, tw.z);
         rng = __float_as_uint(tw.w);
       }
-      const int32_t tri = __float_as_int(hh.w);
-      const bool found = tri >= 0;
       v3 radiance = V(rr.x, rr.y, rr.z);
-
-      float exp_pdf;
-      const v3 le = intersect_light(S, P, org, dir, depth, hh.x, exp_pdf);
-      if (any_gt(le, 0.0f) || !found) {
-        const float mis = (depth == 0 || imp_pdf == CRT_MAXFLOAT) ? 1.0f
-                        : imp_pdf * imp_pdf / (exp_pdf * exp_pdf + imp_pdf * imp_pdf);
-        radiance = vadd(radiance, vscale(vmul(thr, le), mis));
-      } else {
-        const int32_t inst = ld_stream(&st.hit_inst[slot]);
-        const float4* ir = S.inst + 4 * (size_t)inst;
-        float4 m0, m1, m2, m3;
-        ld_record64(ir, m0, m1, m2, m3);
-        const v3 c0 = V(m0.x, m1.x, m2.x), c1 = V(m0.y, m1.y, m2.y), c2 = V(m0.z, m1.z, m2.z);
-        // geometric normal from the stored vertices (same expression as tri_test's nn)
-        const float4* tv = S.tri_verts + kTriStride * (size_t)tri;
-        float4 a, b, c;
-        ld_triangle(tv, a, b, c);
-        const v3 p0 = V(a.x, a.y, a.z), p1 = V(b.x, b.y, b.z), p2 = V(c.x, c.y, c.z);
-        const v3 nraw = cross3(vsub(p0, p2), vsub(p1, p0));
-        const v3 ng = normalize3(V(dot3(c0, nraw), dot3(c1, nraw), dot3(c2, nraw)));
-        org = vadd(org, vscale(dir, hh.x));
-        // SmoothNormal, SURVEY A.4
-        const float4* tn = S.tri_nrm + 3 * (size_t)tri;
-        const v3 n0 = ld_rgb(tn, 0), n1 = ld_rgb(tn, 1), n2 = ld_rgb(tn, 2);
-        v3 ns = vadd(vadd(vscale(n1, hh.y), vscale(n2, hh.z)), vscale(n0, (1.0f - hh.y) - hh.z));
-        ns = normalize3(ns);
-        ns = normalize3(V(dot3(c0, ns), dot3(c1, ns), dot3(c2, ns)));
-        const Frame frame = build_frame(ns);
-
-        const uint32_t mat_id = (uint32_t)__float_as_int(m3.y);
-        Bsdf B;
-        v3 mat_le, absorp;
-        float absorp_k, kd_w = 0.0f, kt_w = 0.0f, le_w = 0.0f;   // texture id + 1, S scale, T scale
-        if (mat_id < S.n_mats) {
-          const float4* mp = S.mats + 8 * (size_t)mat_id;
-          const float4 kc = __ldg(mp), kd = __ldg(mp + 1), ks = __ldg(mp + 2), kt = __ldg(mp + 3);
-          const float4 le4 = __ldg(mp + 4), fc = __ldg(mp + 5), fb = __ldg(mp + 6), ab = __ldg(mp + 7);
-          B.Kc = V(kc.x, kc.y, kc.z); B.Kc_w = kc.w;
-          B.Kd = V(kd.x, kd.y, kd.z);
-          B.Ks = V(ks.x, ks.y, ks.z); B.Ks_w = ks.w;
-          B.Kt = V(kt.x, kt.y, kt.z);
-          B.Fc = V(fc.x, fc.y, fc.z); B.Fb = V(fb.x, fb.y, fb.z);
-          mat_le = V(le4.x, le4.y, le4.z);
-          absorp = V(ab.x, ab.y, ab.z); absorp_k = ab.w;
-          kd_w = kd.w; kt_w = kt.w; le_w = le4.w;
-        } else {   // default grey diffuse (same record as the oracle's k_default_bsdf)
-          B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kd = V(0.8f, 0.8f, 0.8f); B.Ks = V(0, 0, 0); B.Ks_w = 0.0f;
-          B.Kt = V(0, 0, 0); B.Fc = V(-1.0f, 0.0f, 0.0f); B.Fb = V(-1.0f, 0.0f, 1.0f);
-          mat_le = V(0, 0, 0); absorp = V(0, 0, 0); absorp_k = 0.0f;
-        }
-        if (COUNT) cnt.shaded_hits++;
-
-        // base-colour texture (USE_TEXTURES path of PathTrace; SmoothUV)
-        if (TEX) {   // instantiated only for scenes that have textures
-          if (kd_w >= 1.0f && (uint32_t)kd_w - 1u < S.n_tex) {
-            const float2* tu = S.tri_uv + 3 * (size_t)tri;
-            const float2 uv0 = __ldg(tu), uv1 = __ldg(tu + 1), uv2 = __ldg(tu + 2);
-            const float w0 = (1.0f - hh.y) - hh.z;
-            const float su = (uv1.x * hh.y + uv2.x * hh.z) + uv0.x * w0;
-            const float sv = (uv1.y * hh.y + uv2.y * hh.z) + uv0.y * w0;
-            const float ss = kt_w != 0.0f ? kt_w : 1.0f, ts = le_w != 0.0f ? le_w : 1.0f;
-            const float4 tc = tex_lookup(S, (uint32_t)kd_w - 1u, su * ss, sv * ts);
-            B.Kd = vmul(B.Kd, vscale(V(tc.x * tc.x, tc.y * tc.y, tc.z * tc.z), tc.w));
-            if (tc.w != 1.0f) {
-              const float ia = 1.0f - tc.w;
-              B.Kt = V(ia + tc.w * B.Kt.x, ia + tc.w * B.Kt.y, ia + tc.w * B.Kt.z);
-            }
-          }
-        }
-
-        const v3 wo = to_local(V(-dir.x, -dir.y, -dir.z), frame);
-        if (LEAN) {   // host guarantee: no coat, no transmission anywhere in the material table (and so never inside a medium)
-          B.Kc = V(0, 0, 0); B.Kc_w = 0.0f; B.Kt = V(0, 0, 0);
-          inside = false;
-        }
-        radiance = vadd(radiance, vmul(thr, mat_le));
-
-        const v3 nee_k = vadd(B.Kd, vadd(B.Ks_w > CRT_FLT_EPS ? B.Ks : V(0, 0, 0), B.Kc_w > CRT_FLT_EPS ? B.Kc : V(0, 0, 0)));
-        if (S.n_lights > 0 && dot3(nee_k, thr) > 0.0f) {
-          exp_pdf = 1.0f / (float)S.n_lights;
-          int li = (int)(rand_float(rng) * (float)S.n_lights);
-          if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
-          const float4 le_w = __ldg(S.lights + 2 * li), lp = __ldg(S.lights + 2 * li + 1);
-          const bool infinite = lp.w == 0.0f;
-          const v3 to = infinite ? V(lp.x, lp.y, lp.z) : vsub(V(lp.x, lp.y, lp.z), org);
-          const float dist = sqrtf(dot3(to, to));
-          const v3 ldir = sample_light(to, dist, infinite, le_w.w, exp_pdf, rng);
-          const v3 wl = to_local(ldir, frame);
-          const float bpdf = bsdf_pdf_layered(B, wo, wl, thr);
-          imp_pdf = bpdf;
-          const float mis = (exp_pdf == CRT_MAXFLOAT) ? 1.0f : exp_pdf / (exp_pdf * exp_pdf + bpdf * bpdf);
-          const v3 contrib = vscale(vmul(V(le_w.x, le_w.y, le_w.z), eval_bsdf_layered(B, wl, wo, two_sided)), mis);
-          if (any_gt(contrib, CRT_MIN_CONTRIBUTION)) {
-            const float side = dot3(ng, ldir) >= 0.0f ? eps : -eps;
-            sh_o = vadd(vadd(org, vscale(ldir, eps)), vscale(ng, side));
-            sh_d = ldir;
-            sh_tmax = infinite ? CRT_MAXFLOAT : dist;
-            sh_c = vmul(thr, contrib);
-            want_shadow = true;
-          }
-        }
-
-        if (inside) {
-          thr = vmul(thr, V(exp_poly(-hh.x * absorp_k * (1.0f - absorp.x)),
-                            exp_poly(-hh.x * absorp_k * (1.0f - absorp.y)),
-                            exp_poly(-hh.x * absorp_k * (1.0f - absorp.z))));
-        }
-
-        v3 wi;
-        imp_pdf = sample_bsdf_layered<LEAN>(B, wo, wi, thr, inside, rng, two_sided);
-
-        float survive = any_gt(thr, CRT_MIN_THROUGHPUT) ? 1.0f : 0.0f;
-        const bool rr_on = P.russian_roulette && depth >= 3;
-        if (rr_on) survive = minf(fmaf(0.0722f, thr.z, fmaf(0.7152f, thr.y, 0.2126f * thr.x)), 0.95f);
-        const bool dead = rand_float(rng) > survive || all_lt(thr, CRT_MIN_THROUGHPUT);
-        if (!dead && depth + 1 < P.max_depth) {
-          if (rr_on) thr = vscale(thr, 1.0f / survive);
-          dir = normalize3(from_local(wi, frame));
-          const float side = dot3(ng, dir) >= 0.0f ? eps : -eps;
-          org = vadd(vadd(org, vscale(dir, eps)), vscale(ng, side));
-          want_next = true;
-        }
-      }
+      shade_bounce<COUNT, TEX, LEAN>(S, P, depth, two_sided, eps, hh, &st.hit_inst[slot], -1, org, dir, thr, imp_pdf, rng, inside, radiance,
+                                     want_shadow, sh_o, sh_d, sh_c, sh_tmax, want_next, cnt);
       if (FIRST || radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {   // FIRST: this write initialises the slot
         rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
         st_stream(&st.rad[slot], rr);
@@ -1341,6 +1361,67 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
       st_stream(&st.thr[slot], make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng)));
     }
    }
+  }
+  if (COUNT) flush_counters(gcnt, cnt);
+}
+
+// Per-path kernel for the thin end of a wave.  After a few bounces a wave has few paths left, and every wavefront
+// launch then lasts as long as its longest single ray (about 100 us of dependent node fetches, whatever the ray
+// count): eight such launches are a quarter of a frame at the reference's cadence of one sample per Redraw().
+// k_tail(depth) is enqueued before k_shade(depth) from the second bounce on; it does nothing while more than
+// `tail_max` paths are active, and otherwise every lane takes one path and carries it to its end -- shade,
+// shadow ray (any hit), continuation ray (closest hit), shade ... -- with the functions the wavefront kernels use
+// (shade_bounce, traverse), in the order the wavefront applies them, so every path ends with the same bits.
+// k_shade(depth) and everything after it then find nothing to do (k_shade makes the same n <= tail_max test).
+#ifndef CRT_TAIL_MIN_BLOCKS
+#define CRT_TAIL_MIN_BLOCKS 4
+#endif
+template <bool COUNT, bool TEX, bool LEAN>
+__global__ void __launch_bounds__(128, CRT_TAIL_MIN_BLOCKS)
+k_tail(DeviceScene S, DeviceParams P, PathState st, int depth0, uint32_t tail_max, Counters* gcnt)
+{
+  const uint32_t n = st.n_active[depth0];
+  if (n == 0 || n > tail_max) return;
+  const uint32_t* __restrict__ q = st.queue[depth0 & 1];
+  Counters cnt = {};
+  const bool two_sided = P.two_sided != 0;
+  const float eps = S.scene_eps;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = ld_stream(&q[i]);
+    const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]);
+    float4 hh = ld_stream(&st.hit[slot]);
+    float4 rr = ld_stream(&st.rad[slot]);
+    v3 org = V(ro.x, ro.y, ro.z), dir = V(rd.x, rd.y, rd.z), thr = V(tw.x, tw.y, tw.z);
+    float imp_pdf = ro.w;
+    bool inside = (__float_as_int(rd.w) & 1) != 0;
+    uint32_t rng = __float_as_uint(tw.w);
+    v3 radiance = V(rr.x, rr.y, rr.z);
+    const int32_t* inst_src = &st.hit_inst[slot];
+    int32_t inst_reg = -1;
+    for (int depth = depth0;; ++depth) {
+      bool want_shadow = false, want_next = false;
+      v3 sh_o = V(0, 0, 0), sh_d = V(0, 0, 0), sh_c = V(0, 0, 0);
+      float sh_tmax = 0.0f;
+      shade_bounce<COUNT, TEX, LEAN>(S, P, depth, two_sided, eps, hh, inst_src, inst_reg, org, dir, thr, imp_pdf, rng, inside, radiance,
+                                     want_shadow, sh_o, sh_d, sh_c, sh_tmax, want_next, cnt);
+      if (want_shadow) {
+        Hit sh;
+        const bool occluded = traverse<true, COUNT>(S, sh_o, sh_d, sh_tmax, sh, cnt);
+        if (COUNT) cnt.rays_any++;
+        if (!occluded) { radiance.x += sh_c.x; radiance.y += sh_c.y; radiance.z += sh_c.z; }
+      }
+      if (!want_next) break;               // want_next implies depth + 1 < max_depth
+      Hit h;
+      traverse<false, COUNT>(S, org, dir, CRT_MAXFLOAT, h, cnt);
+      if (COUNT) cnt.rays_nearest++;
+      hh = make_float4(h.t, h.u, h.v, __int_as_float(h.tri));
+      inst_src = nullptr;
+      inst_reg = h.inst;
+    }
+    if (radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {
+      rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
+      st_stream(&st.rad[slot], rr);
+    }
   }
   if (COUNT) flush_counters(gcnt, cnt);
 }
@@ -1429,9 +1510,9 @@ k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
 __global__ void __launch_bounds__(256)
 k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_batch, Counters* gcnt)
 {
-  const uint32_t per_sample = P.tiles_x * P.tiles_y * 32u;
+  const uint32_t per_sample = P.n_tiles * 32u;
   for (uint32_t in = blockIdx.x * blockDim.x + threadIdx.x; in < per_sample; in += gridDim.x * blockDim.x) {
-    const uint32_t tile = in >> 5, lane = in & 31u;
+    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
     const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
     const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
     if (px >= P.width || py >= P.height) continue;
@@ -1445,7 +1526,7 @@ k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_b
     }
     accum[(size_t)py * P.width + px] = a;
   }
-  if (gcnt && blockIdx.x == 0 && threadIdx.x == 0)
+  if (gcnt && blockIdx.x == 0 && threadIdx.x == 0 && P.tile0 == 0)      // once per wave (the part that holds tile 0)
     atomicAdd(&gcnt->samples, (unsigned long long)P.width * P.height * n_batch);
 }
 

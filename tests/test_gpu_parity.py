@@ -21,10 +21,19 @@ pytestmark = pytest.mark.gpu
 LEVEL2_TOL = 1e-4   # north_star: "single-sample radiance ... matches within 1e-4"
 
 
-def _pair(desc):
-    """Product view on cuda:0 + oracle on the SAME exported BVH bytes."""
+def _pair(desc, tail_max=None):
+    """Product view on cuda:0 + oracle on the SAME exported BVH bytes.  tail_max: the path count below which the
+    per-path kernel (k_tail) takes a wave over, scaled down for the small test scenes so that they run through the
+    wavefront kernels AND the tail kernel as a 1080p frame does (the knob is read by crt_create)."""
     from oracle.oracle_ffi import OracleScene
-    view = V3d_View(0)
+    if tail_max is not None and "CRT_TAIL_MAX" not in os.environ:
+        os.environ["CRT_TAIL_MAX"] = str(tail_max)
+        try:
+            view = V3d_View(0)
+        finally:
+            del os.environ["CRT_TAIL_MAX"]
+    else:
+        view = V3d_View(0)
     desc.apply(view)
     orc = OracleScene(view.ExportBVH())
     orc.configure(desc)
@@ -50,7 +59,7 @@ SCENES = {
 @pytest.fixture(scope="module", params=list(SCENES))
 def pair(request, product_lib, oracle_lib):
     desc = SCENES[request.param]()
-    view, orc = _pair(desc)
+    view, orc = _pair(desc, tail_max=2048)
     yield desc, view, orc
     view.Remove()
     orc.close()
@@ -650,13 +659,18 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
 # ------------------------------------------------------------------ every A/B knob keeps the result
 
 @pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_PRIMARY_LOCKSTEP=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static",
-                                  "CRT_PIPELINE=1", "CRT_SHADE_LEAN=0"])
+                                  "CRT_PIPELINE=1", "CRT_PIPELINE=0", "CRT_PIPELINE_PARTS=3", "CRT_PIPELINE_PARTS=4", "CRT_SHADE_LEAN=0", "CRT_TAIL=0",
+                                  "CRT_TAIL_MAX=100000000", "CRT_TAIL_MIN_DEPTH=3"])
 def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracle_lib):
     """The environment knobs read by crt_create select alternative kernels / launch structures (unsorted shading,
     a separate generate pass, unfused shadow + extend launches, the static traversal loop, the two-stream half-wave
     pipeline).  They are performance A/B switches: images, work counters and any-hit answers must not change."""
     name, value = knob.split("=")
+    if not name.startswith("CRT_TAIL"):
+        monkeypatch.setenv("CRT_TAIL_MAX", "2048")     # small frame: keep most of the wave in the wavefront kernels
     monkeypatch.setenv(name, value)
+    if name == "CRT_PIPELINE_PARTS":
+        monkeypatch.setenv("CRT_PIPELINE", "1")
     # the lean shading kernel only exists for scenes without coat / transmission: the assembly has neither
     desc = _small_assembly() if name == "CRT_SHADE_LEAN" else scenes.materials_scene(160, 96, depth=8, sphere_res=(32, 16))
     desc.params.SamplesPerBatch = 4
