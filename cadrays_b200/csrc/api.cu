@@ -91,6 +91,7 @@ struct crt_context {
 
   // device scene
   DevBuf<float4> d_arena, d_mats, d_lights, d_env;
+  DevBuf<uint8_t> d_mat_class;
   DevBuf<float2> d_tri_uv;
   DevBuf<float4> d_top_cache;
   DevBuf<uchar4> d_tex;
@@ -141,6 +142,8 @@ struct crt_context {
   // one half overlaps the traversal of the other (CRT_PIPELINE=0/1); traversal CTAs per SM when pipelined
   bool mats_lean = false;       // no material has a coat or transmission: k_shade<.., LEAN> (CRT_SHADE_LEAN=0 disables)
   bool shade_lean = true;
+  bool shade_classes = true;    // k_shade files paths by the shading class of the hit material (CRT_SHADE_CLASSES=0: hit / miss only)
+  bool smem_mats = true;        // material tables of up to kSmemMats records are staged in shared memory by k_shade (CRT_SMEM_MATS=0 disables)
   bool shade_sort = true;       // hit / miss grouping inside k_shade after the first bounce (CRT_SHADE_SORT=0 disables)
   bool primary_lockstep = true; // camera rays walked in lockstep per 8x4 tile instead of per-lane refill (CRT_PRIMARY_LOCKSTEP=0)
   int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
@@ -269,7 +272,7 @@ void update_device_params(crt_context* c)
 
 int ensure_path_slots(crt_context* c, uint64_t need)
 {
-  if (need > 0x7fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
+  if (need > 0x1fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");   // k_shade packs (slot, class) in 32 bits
   if (need <= c->state_capacity) return CRT_OK;
   const size_t n = (size_t)need;
   CRT_CUDA(c->ray_o.ensure(n)); CRT_CUDA(c->ray_d.ensure(n)); CRT_CUDA(c->thr.ensure(n));
@@ -448,9 +451,19 @@ int upload_tables(crt_context* c)
       CRT_CUDA(cudaMemcpyAsync(c->d_mats.p, c->mats.data(), c->mats.size() * sizeof(crt_bsdf), cudaMemcpyHostToDevice, c->stream));
     c->ds.mats = c->d_mats.p; c->ds.n_mats = (uint32_t)c->mats.size();
     c->mats_lean = c->shade_lean;
-    for (const crt_bsdf& m : c->mats)
-      for (int k = 0; k < 3; ++k)
-        if (m.Kc[k] != 0.0f || m.Kt[k] != 0.0f) c->mats_lean = false;
+    std::vector<uint8_t> cls(std::max<size_t>(c->mats.size(), 1), (uint8_t)kClassDiffuse);
+    for (size_t i = 0; i < c->mats.size(); ++i) {
+      const crt_bsdf& m = c->mats[i];
+      bool coat = false, trans = false, spec = false;
+      for (int k = 0; k < 3; ++k) { coat = coat || m.Kc[k] != 0.0f; trans = trans || m.Kt[k] != 0.0f; spec = spec || m.Ks[k] != 0.0f; }
+      if (coat || trans) c->mats_lean = false;
+      cls[i] = (uint8_t)(trans ? kClassTransmissive : coat ? kClassCoat : spec ? kClassGlossy : kClassDiffuse);
+    }
+    CRT_CUDA(c->d_mat_class.ensure(cls.size()));
+    CRT_CUDA(cudaMemcpyAsync(c->d_mat_class.p, cls.data(), cls.size(), cudaMemcpyHostToDevice, c->stream));
+    CRT_CUDA(cudaStreamSynchronize(c->stream));      // `cls` is a local
+    c->ds.mat_class = c->d_mat_class.p;
+    c->ds.mats_in_smem = (c->smem_mats && !c->mats.empty() && c->mats.size() <= kSmemMats) ? 1u : 0u;
     c->mats_dirty = false;
   }
   if (c->lights_dirty) {
@@ -580,13 +593,19 @@ int enqueue_bounces(crt_context* c, const PathState& st, const DeviceParams& dp,
         else if (lean) k_tail<COUNT, false, true><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
         else k_tail<COUNT, false, false><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
       }
-#define CRT_SHADE(TEXV, FIRSTV, SORTV, LEANV) k_shade<COUNT, TEXV, FIRSTV, SORTV, LEANV><<<sg, 128, 0, s>>>(c->ds, dp, st, depth, gc, d_seeds, tail_max)
+#define CRT_SHADE(TEXV, FIRSTV, SORTV, LEANV, CLSV) k_shade<COUNT, TEXV, FIRSTV, SORTV, LEANV, CLSV><<<sg, 128, 0, s>>>(c->ds, dp, st, depth, gc, d_seeds, tail_max)
+      // filing by shading class pays where warps would otherwise mix coat / transmission / base lobes (Cornell: shade -10 %);
+      // with only diffuse and glossy materials the two-pass filing costs more than it returns (C2: shade +7 %)
+      const bool classes = c->shade_classes && !lean;
       if (primary && depth == 0) {
-        if (c->ds.n_tex) CRT_SHADE(true, true, false, false); else if (lean) CRT_SHADE(false, true, false, true); else CRT_SHADE(false, true, false, false);
+        if (c->ds.n_tex) CRT_SHADE(true, true, false, false, false); else if (lean) CRT_SHADE(false, true, false, true, false); else CRT_SHADE(false, true, false, false, false);
       } else if (c->shade_sort && depth > 0) {
-        if (c->ds.n_tex) CRT_SHADE(true, false, true, false); else if (lean) CRT_SHADE(false, false, true, true); else CRT_SHADE(false, false, true, false);
+        if (c->ds.n_tex) { if (classes) CRT_SHADE(true, false, true, false, true); else CRT_SHADE(true, false, true, false, false); }
+        else if (lean) CRT_SHADE(false, false, true, true, false);
+        else if (classes) CRT_SHADE(false, false, true, false, true);
+        else CRT_SHADE(false, false, true, false, false);
       } else {
-        if (c->ds.n_tex) CRT_SHADE(true, false, false, false); else if (lean) CRT_SHADE(false, false, false, true); else CRT_SHADE(false, false, false, false);
+        if (c->ds.n_tex) CRT_SHADE(true, false, false, false, false); else if (lean) CRT_SHADE(false, false, false, true, false); else CRT_SHADE(false, false, false, false, false);
       }
 #undef CRT_SHADE
     }
@@ -797,6 +816,8 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_FUSE")) c->fuse_traversal = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_L2_PERSIST")) c->l2_persist = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_SHADE_LEAN")) c->shade_lean = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_SHADE_CLASSES")) c->shade_classes = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_SMEM_MATS")) c->smem_mats = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_SHADE_SORT")) c->shade_sort = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_LOCKSTEP")) c->primary_lockstep = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_GRID")) c->primary_grid = std::max(1, std::atoi(tv));
@@ -852,7 +873,7 @@ void crt_destroy(crt_context* c)
   collect_spans(c);
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   c->d_arena.release(); c->d_top_cache.release(); c->d_tri_uv.release(); c->d_tex.release(); c->d_tex_table.release();
-  c->d_mats.release(); c->d_lights.release(); c->d_env.release();
+  c->d_mats.release(); c->d_mat_class.release(); c->d_lights.release(); c->d_env.release();
   c->ray_o.release(); c->ray_d.release(); c->thr.release(); c->rad.release(); c->hit.release();
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();
   c->queue0.release(); c->queue1.release(); c->counters.release(); c->seeds.release();

@@ -59,6 +59,13 @@ struct Box {
 // processed, depth first, left first) -- the blob does not depend on the number of threads.
 struct BuildTask { int lo, hi, depth; };
 
+inline int env_int(const char* name, int dflt)
+{
+  const char* v = std::getenv(name);
+  return v ? std::max(1, std::atoi(v)) : dflt;
+}
+
+
 // Runs fn(part, begin, end) on `parts` contiguous slices of [lo, hi), each on its own std::thread.  Used for the
 // passes over the few very large nodes at the top of a big tree; plain threads rather than OpenMP regions because
 // the regions are short and frequent, and spinning OpenMP workers between them slowed the serial code in between
@@ -184,6 +191,18 @@ void build_range(std::vector<Prim>& prims, int lo, int hi, int depth0, int leaf_
         if (cnt == 0 || right_count[b + 1] == 0) continue;
         float cost = half_area(acc.lo, acc.hi) * (float)cnt + right_area[b + 1] * (float)right_count[b + 1];
         if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
+      }
+    }
+    {   // experiment: SAH termination (CRT_SAH_LEAF = largest leaf, CRT_SAH_CT = node cost in units of 1/16 triangle test)
+      static const int sah_leaf = std::getenv("CRT_SAH_LEAF") ? std::atoi(std::getenv("CRT_SAH_LEAF")) : 0;
+      static const float sah_ct = std::getenv("CRT_SAH_CT") ? (float)std::atoi(std::getenv("CRT_SAH_CT")) / 16.0f : 1.0f;
+      if (sah_leaf > 0 && count <= sah_leaf && best_axis >= 0) {
+        const float pa = half_area(nb.lo, nb.hi);
+        if ((float)count * pa <= best_cost + sah_ct * pa) {
+          nd.leaf = true; nd.a = w.lo; nd.b = w.hi - 1;
+          nodes[w.node] = nd;
+          continue;
+        }
       }
     }
     int mid;
@@ -376,7 +395,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
       for (int k = 0; k < 3; ++k) { p.lo[k] = b.lo[k]; p.hi[k] = b.hi[k]; p.c[k] = 0.5f * (b.lo[k] + b.hi[k]); }
       p.id = (uint32_t)t;
     }
-    build_tree(prims, kBottomLeafSize, kBottomBins, trees[mi].nodes, trees[mi].depth);
+    build_tree(prims, env_int("CRT_LEAF_SIZE", kBottomLeafSize), env_int("CRT_BOTTOM_BINS", kBottomBins), trees[mi].nodes, trees[mi].depth);
     trees[mi].order.resize(nt);
     for (size_t t = 0; t < nt; ++t) trees[mi].order[t] = prims[t].id;
     trees[mi].built = true;
@@ -474,7 +493,7 @@ bool build_blob(const HostScene& scene, std::vector<uint8_t>& blob, std::string&
   lap("instance world boxes");
   std::vector<TreeNode> top;
   int top_depth = 0;
-  build_tree(iprims, kTopLeafSize, kTopBins, top, top_depth);
+  build_tree(iprims, kTopLeafSize, env_int("CRT_TOP_BINS", kTopBins), top, top_depth);
   if (quad) top = collapse_to_quad(top, top_depth);
   const uint32_t n_top = (uint32_t)top.size();
   const uint32_t n_nodes = n_inst ? n_top + n_bottom_nodes : 0;

@@ -86,8 +86,12 @@ struct BlobView {
   const int32_t* inst_meta;
 };
 
-// Builder constants (binned SAH, leaf size 5, depth 32; top level leaf size 1).
-constexpr int kBottomLeafSize = 5;
+// Builder constants (binned SAH, depth 32; top level leaf size 1).  OCCT's BVH_BinnedBuilder stops at 5
+// triangles per leaf; here the default is 2: a triangle test costs the traversal kernels about 1.8 node visits (it runs
+// with half the lanes of the node loop), and the smaller leaves measured 2.3 % less traversal time on config C2, 2.2 %
+// on C5 instanced, 0.5 % on C5 flattened for 30 % more node memory (profiles/README.md).  CRT_LEAF_SIZE=5 restores
+// OCCT's value; hits do not depend on it except for exact-distance ties.
+constexpr int kBottomLeafSize = 2;
 constexpr int kTopLeafSize    = 1;
 constexpr int kMaxTreeDepth   = 32;
 constexpr int kBottomBins     = 48;

@@ -36,6 +36,8 @@ struct DeviceScene {
   const float4* __restrict__ tri_nrm;     // 3 x float4 per triangle
   const float4* __restrict__ inst;        // 4 x float4 per instance
   const float4* __restrict__ mats;        // 8 x float4 per material (crt_bsdf)
+  const uint8_t* __restrict__ mat_class;  // shading class of each material (kClass*)
+  uint32_t mats_in_smem;                  // k_shade stages the material table in shared memory (n_mats <= kSmemMats)
   const float4* __restrict__ lights;      // 2 x float4 per light (shader form)
   const float4* __restrict__ env;         // lat-long texels, rgb_
   const float2* __restrict__ tri_uv;      // 3 x float2 per triangle
@@ -1114,7 +1116,7 @@ __device__ __forceinline__ void shade_bounce(const DeviceScene& S, const DeviceP
                                              const float eps, const float4 hh, const int32_t* inst_src, const int32_t inst_reg,
                                              v3& org, v3& dir, v3& thr, float& imp_pdf, uint32_t& rng, bool& inside, v3& radiance,
                                              bool& want_shadow, v3& sh_o, v3& sh_d, v3& sh_c, float& sh_tmax, bool& want_next,
-                                             Counters& cnt)
+                                             Counters& cnt, const float4* smem_mats = nullptr)
 {
   const int32_t tri = __float_as_int(hh.w);
   const bool found = tri >= 0;
@@ -1152,9 +1154,15 @@ __device__ __forceinline__ void shade_bounce(const DeviceScene& S, const DeviceP
     v3 mat_le, absorp;
     float absorp_k, kd_w = 0.0f, kt_w = 0.0f, le_w = 0.0f;   // texture id + 1, S scale, T scale
     if (mat_id < S.n_mats) {
-      const float4* mp = S.mats + 8 * (size_t)mat_id;
-      const float4 kc = __ldg(mp), kd = __ldg(mp + 1), ks = __ldg(mp + 2), kt = __ldg(mp + 3);
-      const float4 le4 = __ldg(mp + 4), fc = __ldg(mp + 5), fb = __ldg(mp + 6), ab = __ldg(mp + 7);
+      float4 kc, kd, ks, kt, le4, fc, fb, ab;
+      if (smem_mats) {   // warp-uniform: the whole table is staged in shared memory (small scenes)
+        const float4* mp = smem_mats + 8 * (size_t)mat_id;
+        kc = mp[0]; kd = mp[1]; ks = mp[2]; kt = mp[3]; le4 = mp[4]; fc = mp[5]; fb = mp[6]; ab = mp[7];
+      } else {
+        const float4* mp = S.mats + 8 * (size_t)mat_id;
+        kc = __ldg(mp); kd = __ldg(mp + 1); ks = __ldg(mp + 2); kt = __ldg(mp + 3);
+        le4 = __ldg(mp + 4); fc = __ldg(mp + 5); fb = __ldg(mp + 6); ab = __ldg(mp + 7);
+      }
       B.Kc = V(kc.x, kc.y, kc.z); B.Kc_w = kc.w;
       B.Kd = V(kd.x, kd.y, kd.z);
       B.Ks = V(ks.x, ks.y, ks.z); B.Ks_w = ks.w;
@@ -1250,14 +1258,21 @@ __device__ __forceinline__ void shade_bounce(const DeviceScene& S, const DeviceP
 #ifndef CRT_SHADE_MIN_BLOCKS
 #define CRT_SHADE_MIN_BLOCKS 8
 #endif
-// SORT (bounces after the first): a CTA takes kShadeBatch queue entries at a time, files them in shared memory
-// under "hit a surface" (from the front) and "missed" (from the back), then shades the two groups one after the
-// other, so that the lanes of a warp run the same branch of the bounce.  Only the order changes.
+// SORT (bounces after the first): a CTA takes kShadeBatch queue entries at a time and files them in shared memory by
+// shading class -- diffuse only / diffuse + glossy / coated / transmissive, taken from the material of the hit
+// (DeviceScene::mat_class), and "missed" last -- each class starting on a warp boundary, then shades the list in that
+// order, so that the lanes of a warp run the same lobes of the layered BSDF.  Without a class table the classes
+// are just "hit" and "missed".  Only the order changes.
 #ifndef CRT_SHADE_BATCH
 #define CRT_SHADE_BATCH 512
 #endif
 constexpr uint32_t kShadeBatch = CRT_SHADE_BATCH;
-template <bool COUNT, bool TEX, bool FIRST, bool SORT, bool LEAN>
+constexpr int kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassCoat = 3, kClassTransmissive = 4, kNumClasses = 5;
+constexpr uint32_t kShadeListSize = kShadeBatch + 32u * (kNumClasses - 1);
+// material table in shared memory (north_star: "the material table staged in shared memory"): tables of up to
+// kSmemMats records (4 KB) are copied once per CTA; larger ones (C2: 1001 materials = 125 KB) stay in L1 / L2
+constexpr uint32_t kSmemMats = 32;
+template <bool COUNT, bool TEX, bool FIRST, bool SORT, bool LEAN, bool CLASSES>
 __global__ void __launch_bounds__(128, CRT_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, const uint32_t* __restrict__ seeds, uint32_t tail_max)
 {
@@ -1268,13 +1283,76 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
   Counters cnt = {};
   const bool two_sided = P.two_sided != 0;
   const float eps = S.scene_eps;
-  __shared__ uint32_t s_list[SORT ? kShadeBatch : 1];
-  __shared__ uint32_t s_cnt[2];
+  __shared__ uint32_t s_list[SORT ? (CLASSES ? kShadeListSize : kShadeBatch) : 1];
+  __shared__ uint32_t s_tmp[SORT && CLASSES ? kShadeBatch : 1];
+  __shared__ uint32_t s_cnt[kNumClasses], s_cur[kNumClasses], s_off[kNumClasses + 1];
+  __shared__ float4 s_mats[LEAN ? 1 : 8 * kSmemMats];
+  const float4* smem_mats = nullptr;
+  if (!LEAN && S.mats_in_smem) {
+    for (uint32_t k = threadIdx.x; k < 8u * S.n_mats; k += blockDim.x) s_mats[k] = __ldg(S.mats + k);
+    __syncthreads();
+    smem_mats = s_mats;
+  }
   const uint32_t batch = SORT ? kShadeBatch : 128u;
   for (uint32_t bbase = blockIdx.x * batch; bbase < n; bbase += gridDim.x * batch) {
    uint32_t n_iter = 1, n_hit = 0, n_hit_pad = 0, n_miss = 0;
-   if (SORT) {
+   if (SORT && CLASSES) {
      __syncthreads();                       // the previous batch's list is no longer read
+     if (threadIdx.x < kNumClasses) { s_cnt[threadIdx.x] = 0; s_cur[threadIdx.x] = 0; }
+     __syncthreads();
+     const uint32_t lane = threadIdx.x & 31u;
+     const unsigned below = (1u << lane) - 1u;
+     // pass 1: slot and class of every entry of the batch (slot | class << 29 in s_tmp: slots are < 2^29), class sizes
+#pragma unroll 1
+     for (uint32_t k = 0; k < kShadeBatch / 128u; ++k) {
+       const uint32_t e = bbase + k * 128u + threadIdx.x;
+       uint32_t sl = 0;
+       int cls = -1;
+       if (e < n) {
+         sl = ld_stream(&q[e]);
+         cls = kClassMiss;
+         if (__float_as_int(ld_stream(&st.hit[sl]).w) >= 0) {
+           cls = kClassDiffuse;
+           {
+             const int32_t inst = ld_stream(&st.hit_inst[sl]);
+             const uint32_t mid = (uint32_t)__float_as_int(__ldg(S.inst + 4 * (size_t)inst + 3).y);
+             if (mid < S.n_mats) cls = (int)__ldg(S.mat_class + mid);
+           }
+         }
+       }
+       s_tmp[k * 128u + threadIdx.x] = cls < 0 ? 0xffffffffu : (sl | ((uint32_t)cls << 29));
+#pragma unroll
+       for (int c = 0; c < kNumClasses; ++c) {
+         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+         if (lane == 0 && m) atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
+       }
+     }
+     __syncthreads();
+     if (threadIdx.x == 0) {                // class order in the list: 1, 2, 3, 4, then the misses; each on a warp boundary
+       uint32_t o = 0;
+       for (int c = 1; c <= kNumClasses; ++c) { const int cc = c % kNumClasses; s_off[cc] = o; o += (s_cnt[cc] + 31u) & ~31u; }
+       s_off[kNumClasses] = o;
+     }
+     __syncthreads();
+     // pass 2: scatter (each thread re-reads the entries it wrote)
+#pragma unroll 1
+     for (uint32_t k = 0; k < kShadeBatch / 128u; ++k) {
+       const uint32_t v = s_tmp[k * 128u + threadIdx.x];
+       const int cls = v == 0xffffffffu ? -1 : (int)(v >> 29);
+#pragma unroll
+       for (int c = 0; c < kNumClasses; ++c) {
+         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+         uint32_t base = 0;
+         if (lane == 0 && m) base = atomicAdd(&s_cur[c], (uint32_t)__popc(m));
+         base = __shfl_sync(0xffffffffu, base, 0);
+         if (cls == c) s_list[s_off[c] + base + __popc(m & below)] = v & 0x1fffffffu;
+       }
+     }
+     __syncthreads();
+     n_iter = (s_off[kNumClasses] + 127u) / 128u;
+   }
+   if (SORT && !CLASSES) {                  // two classes, one pass: hits from the front of the list, misses from the back
+     __syncthreads();
      if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
      __syncthreads();
      const uint32_t lane = threadIdx.x & 31u;
@@ -1303,7 +1381,14 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
     uint32_t i = bbase + threadIdx.x;
     bool valid = i < n;
     uint32_t slot = 0;
-    if (SORT) {
+    if (SORT && CLASSES) {
+      const uint32_t e = it * 128u + threadIdx.x;
+      valid = false;
+#pragma unroll
+      for (int c = 0; c < kNumClasses; ++c) valid = valid || (e >= s_off[c] && e < s_off[c] + s_cnt[c]);
+      if (valid) slot = s_list[e];
+    }
+    if (SORT && !CLASSES) {
       const uint32_t e = it * 128u + threadIdx.x;
       valid = e < n_hit || (e >= n_hit_pad && e < n_hit_pad + n_miss);
       if (valid) slot = e < n_hit ? s_list[e] : s_list[kShadeBatch - 1u - (e - n_hit_pad)];
@@ -1340,7 +1425,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
       }
       v3 radiance = V(rr.x, rr.y, rr.z);
       shade_bounce<COUNT, TEX, LEAN>(S, P, depth, two_sided, eps, hh, &st.hit_inst[slot], -1, org, dir, thr, imp_pdf, rng, inside, radiance,
-                                     want_shadow, sh_o, sh_d, sh_c, sh_tmax, want_next, cnt);
+                                     want_shadow, sh_o, sh_d, sh_c, sh_tmax, want_next, cnt, smem_mats);
       if (FIRST || radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {   // FIRST: this write initialises the slot
         rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
         st_stream(&st.rad[slot], rr);
