@@ -114,6 +114,7 @@ PROTOTYPES = {
     "crt_stats_get": (C.c_int, [_ctx, C.POINTER(crt_stats)]),
     "crt_timing_enable": (C.c_int, [_ctx, C.c_int]),
     "crt_timing_get": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "crt_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
     "crt_scene_bytes": (C.c_int, [_ctx, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "crt_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "crt_commit_stats": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),

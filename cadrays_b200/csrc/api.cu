@@ -156,11 +156,13 @@ struct crt_context {
   int tail_min_depth = 1;
   // a wave split into `parts` ranges of 8x4 pixel tiles, each on its own stream: every launch of a thin wave ends
   // with a tail in which a few long rays finish while most SMs idle, and the parts fill each other's tails.
-  // pipeline: 0 = never, 1 = always, 2 = automatic (waves of at most pipeline_auto_paths paths: the reference's
-  // cadence of one sample per Redraw).  CRT_PIPELINE / CRT_PIPELINE_PARTS / CRT_PIPELINE_AUTO_PATHS.
+  // pipeline: 0 = never, 1 = always, 2 = automatic: waves of at most pipeline_auto_paths paths, unless per-family timing
+  // is on (crt_timing_enable: a kernel's duration is only defined while kernels do not overlap, so timed waves run
+  // unsplit on one stream).  Measured with two parts, 1080p: C2 +3.4 % at 16 spp per wave and 405 -> 432 frames/s at
+  // one sample per Redraw, C5 flattened +6.5 %, C3 +1.5 %, Cornell +-0.  CRT_PIPELINE / CRT_PIPELINE_PARTS / CRT_PIPELINE_AUTO_PATHS.
   int pipeline = 2;
   int pipeline_parts = 2;
-  uint64_t pipeline_auto_paths = 5ull << 20;
+  uint64_t pipeline_auto_paths = 1ull << 40;
   int pipeline_trace_ctas = 0;   // cap of the traversal grids (CTAs per SM) while split; 0 = none
   static constexpr int kMaxParts = 4;
   cudaStream_t side_stream[kMaxParts - 1] = {};
@@ -176,6 +178,7 @@ struct crt_context {
   std::vector<cudaEvent_t> event_pool;
   double family_ms[F_COUNT] = {};
   uint64_t family_launches[F_COUNT] = {};
+  uint64_t kernel_launches = 0;   // kernels enqueued since crt_stats_reset (always counted; crt_launch_count)
 };
 
 namespace {
@@ -220,6 +223,7 @@ struct SpanGuard {
   crt_context* c; int family; cudaStream_t s; cudaEvent_t a = nullptr;
   SpanGuard(crt_context* c_, int f, cudaStream_t s_ = nullptr) : c(c_), family(f), s(s_ ? s_ : c_->stream)
   {
+    if (family != F_RENDER) c->kernel_launches++;      // every guarded scope holds one kernel launch (k_tail is added where it is launched)
     if (c->timing_on) { a = get_event(c); cudaEventRecord(a, s); }
   }
   ~SpanGuard()
@@ -588,6 +592,7 @@ int enqueue_bounces(crt_context* c, const PathState& st, const DeviceParams& dp,
       // the thin end of the wave: k_tail finishes the paths of this bounce when few are left, k_shade then skips them
       const uint32_t tail_max = (c->tail && !QUAD && depth >= std::max(1, c->tail_min_depth)) ? c->tail_max : 0u;   // k_tail walks the binary layout
       if (tail_max) {
+        c->kernel_launches++;
         const int tg = c->sm_count * CRT_TAIL_MIN_BLOCKS;
         if (c->ds.n_tex) k_tail<COUNT, true, false><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
         else if (lean) k_tail<COUNT, false, true><<<tg, 128, 0, s>>>(c->ds, dp, st, depth, tail_max, gc);
@@ -631,7 +636,7 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, cons
   const uint32_t n_tiles = c->dp.tiles_x * c->dp.tiles_y;
   const uint64_t paths = (uint64_t)n_tiles * 32u * n_batch;
   int parts = 1;
-  if (!adaptive && c->side_stream[0] && (c->pipeline == 1 || (c->pipeline == 2 && paths <= c->pipeline_auto_paths)))
+  if (!adaptive && c->side_stream[0] && (c->pipeline == 1 || (c->pipeline == 2 && paths <= c->pipeline_auto_paths && !c->timing_on)))
     parts = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(c->pipeline_parts, (int)crt_context::kMaxParts)), std::max(1u, n_tiles / 64u));
   CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(uint32_t) * ((size_t)(parts - 1) * kCounterWords + 4 * depth_max + 2), c->stream));
   c->last_parts.clear();
@@ -1441,6 +1446,7 @@ int crt_stats_enable(crt_context* c, int on) { CRT_REQUIRE(c, "null context"); c
 
 int crt_stats_reset(crt_context* c)
 {
+  if (c) c->kernel_launches = 0;
   CRT_REQUIRE(c, "null context");
   int rc = set_device(c);
   if (rc) return rc;
@@ -1459,6 +1465,13 @@ int crt_stats_get(crt_context* c, crt_stats* out)
   static_assert(sizeof(Counters) == sizeof(crt_stats), "counter layout");
   CRT_CUDA(cudaStreamSynchronize(c->stream));
   CRT_CUDA(cudaMemcpy(out, c->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+  return CRT_OK;
+}
+
+int crt_launch_count(crt_context* c, uint64_t* out)
+{
+  CRT_REQUIRE(c && out, "null argument");
+  *out = c->kernel_launches;
   return CRT_OK;
 }
 

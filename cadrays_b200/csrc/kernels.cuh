@@ -1536,6 +1536,7 @@ __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
 k_connect(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n = st.n_shadow[depth];
+  if (n == 0) return;
   Counters cnt = {};
   if (PERSISTENT) {
     ConnectPolicy pol{ st };
@@ -1584,6 +1585,7 @@ k_trace_dual(DeviceScene S, PathState st, int depth, Counters* gcnt)
 {
   const uint32_t n_ext = st.n_active[depth];
   const uint32_t n_sh = st.n_shadow[depth - 1];
+  if (n_ext + n_sh == 0) return;           // the wave has ended (or k_tail has taken it over): skip the work-counter atomics
   Counters cnt = {};
   DualPolicy pol{ ExtendPolicy{ st, st.queue[depth & 1] }, ConnectPolicy{ st }, n_ext };
   trace_persistent<2, COUNT, QUAD>(S, n_ext + n_sh, st.work_extend + depth, cnt, pol);

@@ -558,6 +558,12 @@ class V3d_View:
         names = ("generate", "extend", "shade", "connect", "resolve", "render")
         return {n: (ms[i], int(ln[i])) for i, n in enumerate(names)}
 
+    def LaunchCount(self) -> int:
+        """Kernels enqueued by this view's context since ResetStats()."""
+        n = C.c_uint64()
+        check(self._lib.crt_launch_count(self._ctx, C.byref(n)))
+        return int(n.value)
+
     def SceneBytes(self):
         """(bytes the traversal kernels read, bytes of the whole committed scene) in device memory."""
         a, b = C.c_size_t(), C.c_size_t()

@@ -353,8 +353,12 @@ int crt_stats_get(crt_context* ctx, crt_stats* out);
 /* Device time (ms, CUDA events on the context stream) spent in each kernel
  * family since crt_stats_reset: [0] generate, [1] extend (nearest hit),
  * [2] shade, [3] connect (any hit), [4] resolve+display, [5] whole render calls.
- * Only collected while crt_timing_enable(ctx, 1). */
+ * Only collected while crt_timing_enable(ctx, 1).  While it is on, a wave runs unsplit on one stream (normally its
+ * two halves share the GPU on two streams): a kernel's duration is only defined while kernels do not overlap, so timed
+ * renders are a few per cent slower than untimed ones. */
 int crt_timing_enable(crt_context* ctx, int on);
+/* Kernels this context has enqueued since crt_stats_reset (always counted). */
+int crt_launch_count(crt_context* ctx, uint64_t* out_launches);
 int crt_timing_get(crt_context* ctx, double ms[6], uint64_t launches[6]);
 /* Bytes of the committed scene in device memory: `traversal` = what SceneNearestHit / SceneAnyHit read (nodes,
  * triangle vertices, instance records), `total` adds the shading-side arrays (vertex normals, texels, materials,
