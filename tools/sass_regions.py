@@ -21,9 +21,21 @@ def main():
                      int(r[ix["# Samples"]]), int(r[ix["stall_long_sb"]])))
     tot_i = sum(d[2] for d in data); tot_s = sum(d[4] for d in data)
     ranges = []
-    for a in sys.argv[2:]:
+    for a in [x for x in sys.argv[2:] if not x.startswith("--")]:
         s, e, label = a.split(":")
         ranges.append((int(s, 16), int(e, 16), label))
+    if "--blocks" in sys.argv:          # shares per 256-byte block of SASS: enough to tell the node loop, the triangle loop, refill ... apart
+        import collections
+        blk = collections.OrderedDict()
+        for off, src, ie, te, sm, lsb in data:
+            b = blk.setdefault(off >> 8, [0, 0, 0, 0, src])
+            b[0] += ie; b[1] += te; b[2] += sm; b[3] += lsb
+        print("total warp instructions %d, samples %d" % (tot_i, tot_s))
+        for k, b in blk.items():
+            if b[0]:
+                print("%05x  %6.2f%% of warp inst  %5.1f lanes  %6.2f%% of samples (long_sb %5.2f%%)  %s" %
+                      (k << 8, 100.0 * b[0] / tot_i, b[1] / max(b[0], 1), 100.0 * b[2] / tot_s, 100.0 * b[3] / tot_s, b[4][:60]))
+        return
     if not ranges:
         for off, src, ie, te, sm, lsb in data:
             print("%05x %6.2f%% inst %5.1f lanes %6.2f%% samples  %s" % (off, 100.0 * ie / tot_i, te / max(ie, 1), 100.0 * sm / tot_s, src))
