@@ -121,7 +121,7 @@ struct crt_context {
   uint32_t rng_hi = 0, rng_lo = 0; uint64_t rng_index = 0; bool rng_valid = false;
 
   // adaptive screen sampling (crt_params.adaptive_sampling): per-tile state, see kernels.cuh
-  DevBuf<uint32_t> ad_count, ad_err, ad_cum, ad_qoff, ad_seeds;
+  DevBuf<uint32_t> ad_count, ad_err, ad_cum, ad_qoff, ad_seeds, ad_cum_own;
   DevBuf<float> ad_even;
   std::vector<uint32_t> ad_h_seeds;  // frame seeds of sample indices first_sample + [0, size)
   size_t ad_seeds_uploaded = 0;
@@ -681,17 +681,26 @@ int dispatch_batch(crt_context* c, uint32_t n, const uint32_t* d_seeds, const Ad
 // Adaptive screen sampling: n_samples x adaptive_tiles tile samples, in waves of at most
 // samples-per-batch x (number of tiles); each wave is dealt out on the device from the error
 // estimates the previous wave left (kernels.cuh).
-int render_adaptive(crt_context* c, uint32_t n_samples)
+// Adaptive screen sampling, host side.  adaptive_begin() sizes and (after a reset) clears the per-tile state and returns
+// the device view of it; adaptive_wave() enqueues one wave of `budget` tile samples (frame seeds, allocation, the wave).
+// A crt_group calls the same two steps on every member with (rank, n_members) set and runs the exchange step
+// (k_adaptive_error_peers) between the waves; for one context the wave's own resolve pass updates the estimate.
+struct AdaptivePlan { uint32_t nt; uint64_t per_unit, wave_cap; };
+
+int adaptive_begin(crt_context* c, uint32_t n_samples, uint32_t rank, uint32_t n_members, AdaptiveState* A, AdaptivePlan* plan)
 {
   const uint32_t ntx = (c->width + kAdaptiveTile - 1) / kAdaptiveTile, nty = (c->height + kAdaptiveTile - 1) / kAdaptiveTile;
   const uint32_t nt = ntx * nty;
   const uint64_t per_unit = c->params.adaptive_tiles > 0 ? (uint64_t)c->params.adaptive_tiles : nt;
   const uint64_t wave_cap = (uint64_t)auto_batch(c) * nt;
-  if (wave_cap * kAdaptiveSlots > 0x7fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
-  int rc = ensure_path_slots(c, std::min<uint64_t>(wave_cap, per_unit * n_samples) * kAdaptiveSlots);
+  // a member renders at most ceil(k / n) samples of a tile that receives k: one wave's share fits wave_cap + nt tile samples
+  const uint64_t own_cap = n_members > 1 ? wave_cap + nt : std::min<uint64_t>(wave_cap, per_unit * n_samples);
+  if (own_cap * kAdaptiveSlots > 0x1fffffffull) return fail(CRT_ERR_INVALID_ARG, "batch too large");
+  int rc = ensure_path_slots(c, own_cap * kAdaptiveSlots);
   if (rc) return rc;
   CRT_CUDA(c->ad_count.ensure(nt)); CRT_CUDA(c->ad_err.ensure(nt));
   CRT_CUDA(c->ad_cum.ensure(nt + 1)); CRT_CUDA(c->ad_qoff.ensure(nt + 1));
+  if (n_members > 1) CRT_CUDA(c->ad_cum_own.ensure(nt + 1));
   CRT_CUDA(c->ad_even.ensure((size_t)c->width * c->height));
   if (c->ad_clear) {
     CRT_CUDA(cudaMemsetAsync(c->ad_count.p, 0, sizeof(uint32_t) * nt, c->stream));
@@ -700,35 +709,54 @@ int render_adaptive(crt_context* c, uint32_t n_samples)
     c->ad_h_seeds.clear(); c->ad_seeds_uploaded = 0; c->ad_bound = 0; c->ad_wave = 0;
     c->ad_clear = false;
   }
+  A->count = c->ad_count.p; A->err = c->ad_err.p; A->cum = c->ad_cum.p; A->qoff = c->ad_qoff.p; A->even = c->ad_even.p;
+  A->ntx = ntx; A->nty = nty; A->nt = nt; A->first_parity = (uint32_t)(c->first_sample & 1u);
+  A->cum_own = n_members > 1 ? c->ad_cum_own.p : c->ad_cum.p;
+  A->rank = rank; A->n_members = n_members;
+  plan->nt = nt; plan->per_unit = per_unit; plan->wave_cap = wave_cap;
+  return CRT_OK;
+}
+
+int adaptive_wave(crt_context* c, const AdaptiveState& A, uint32_t budget)
+{
+  // no tile can receive more than 32 * budget / nt + 1 samples in a wave (weights are clamped to a 1:32 range)
+  c->ad_bound += 32ull * budget / A.nt + 2;
+  if (c->ad_bound > (1ull << 26)) return fail(CRT_ERR_INVALID_ARG, "adaptive accumulation too long; reset it");
+  while (c->ad_h_seeds.size() < c->ad_bound) c->ad_h_seeds.push_back(frame_seed(c, c->first_sample + c->ad_h_seeds.size()));
+  if (c->ad_seeds.n < c->ad_h_seeds.size()) {
+    // the wave in flight may still read the old table
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    CRT_CUDA(c->ad_seeds.ensure(std::max<size_t>(2 * c->ad_h_seeds.size(), 4096)));
+    c->ad_seeds_uploaded = 0;
+  }
+  CRT_CUDA(cudaMemcpyAsync(c->ad_seeds.p + c->ad_seeds_uploaded, c->ad_h_seeds.data() + c->ad_seeds_uploaded,
+                           sizeof(uint32_t) * (c->ad_h_seeds.size() - c->ad_seeds_uploaded), cudaMemcpyHostToDevice, c->stream));
+  c->ad_seeds_uploaded = c->ad_h_seeds.size();
+  k_adaptive_allocate<<<1, 1024, 0, c->stream>>>(A, c->dp, budget, c->ad_wave);
+  int rc = dispatch_batch(c, budget, c->ad_seeds.p, &A);
+  if (rc) return rc;
+  c->ad_wave++;
+  return CRT_OK;
+}
+
+int render_adaptive(crt_context* c, uint32_t n_samples)
+{
   AdaptiveState A;
-  A.count = c->ad_count.p; A.err = c->ad_err.p; A.cum = c->ad_cum.p; A.qoff = c->ad_qoff.p; A.even = c->ad_even.p;
-  A.ntx = ntx; A.nty = nty; A.nt = nt; A.first_parity = (uint32_t)(c->first_sample & 1u);
+  AdaptivePlan plan;
+  int rc = adaptive_begin(c, n_samples, 0, 1, &A, &plan);
+  if (rc) return rc;
   SpanGuard whole(c, F_RENDER);
-  for (uint64_t left = per_unit * n_samples; left > 0;) {
-    const uint32_t budget = (uint32_t)std::min<uint64_t>(left, wave_cap);
-    // no tile can receive more than 32 * budget / nt + 1 samples in a wave (weights are clamped to a 1:32 range)
-    c->ad_bound += 32ull * budget / nt + 2;
-    if (c->ad_bound > (1ull << 26)) return fail(CRT_ERR_INVALID_ARG, "adaptive accumulation too long; reset it");
-    while (c->ad_h_seeds.size() < c->ad_bound) c->ad_h_seeds.push_back(frame_seed(c, c->first_sample + c->ad_h_seeds.size()));
-    if (c->ad_seeds.n < c->ad_h_seeds.size()) {
-      // the wave in flight may still read the old table
-      CRT_CUDA(cudaStreamSynchronize(c->stream));
-      CRT_CUDA(c->ad_seeds.ensure(std::max<size_t>(2 * c->ad_h_seeds.size(), 4096)));
-      c->ad_seeds_uploaded = 0;
-    }
-    CRT_CUDA(cudaMemcpyAsync(c->ad_seeds.p + c->ad_seeds_uploaded, c->ad_h_seeds.data() + c->ad_seeds_uploaded,
-                             sizeof(uint32_t) * (c->ad_h_seeds.size() - c->ad_seeds_uploaded), cudaMemcpyHostToDevice, c->stream));
-    c->ad_seeds_uploaded = c->ad_h_seeds.size();
-    k_adaptive_allocate<<<1, 1024, 0, c->stream>>>(A, c->dp, budget, c->ad_wave);
-    if ((rc = dispatch_batch(c, budget, c->ad_seeds.p, &A))) return rc;
-    c->ad_wave++;
+  for (uint64_t left = plan.per_unit * n_samples; left > 0;) {
+    const uint32_t budget = (uint32_t)std::min<uint64_t>(left, plan.wave_cap);
+    if ((rc = adaptive_wave(c, A, budget))) return rc;
     left -= budget;
   }
   c->next_sample += n_samples;
   return CRT_OK;
 }
 
-int render_impl(crt_context* c, uint32_t n_samples)
+// what every render call checks and refreshes before it enqueues waves
+int render_prepare(crt_context* c)
 {
   if (!c->has_layout || c->geometry_dirty) return fail(CRT_ERR_STATE, "crt_render before crt_commit");
   if (!c->width || !c->height) return fail(CRT_ERR_STATE, "crt_render before crt_resize");
@@ -737,8 +765,15 @@ int render_impl(crt_context* c, uint32_t n_samples)
   if (rc) return rc;
   if ((rc = upload_tables(c))) return rc;
   update_device_params(c);
-  if (n_samples == 0) return CRT_OK;
   CRT_CUDA(c->counters.ensure(crt_context::kMaxParts * kCounterWords));
+  return CRT_OK;
+}
+
+int render_impl(crt_context* c, uint32_t n_samples)
+{
+  int rc = render_prepare(c);
+  if (rc) return rc;
+  if (n_samples == 0) return CRT_OK;
   if (c->params.adaptive_sampling) return render_adaptive(c, n_samples);
   const uint32_t batch = std::min(auto_batch(c), n_samples);
   if ((rc = ensure_path_state(c, batch))) return rc;
@@ -883,7 +918,7 @@ void crt_destroy(crt_context* c)
   c->sh_o.release(); c->sh_d.release(); c->sh_c.release(); c->hit_inst.release();
   c->queue0.release(); c->queue1.release(); c->counters.release(); c->seeds.release();
   c->accum_internal.release(); c->d_ldr.release(); c->d_hdr.release(); c->d_counters.release();
-  c->ad_count.release(); c->ad_err.release(); c->ad_cum.release(); c->ad_qoff.release(); c->ad_seeds.release(); c->ad_even.release();
+  c->ad_count.release(); c->ad_err.release(); c->ad_cum.release(); c->ad_qoff.release(); c->ad_seeds.release(); c->ad_even.release(); c->ad_cum_own.release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int k = 0; k < crt_context::kMaxParts - 1; ++k) {
     if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);

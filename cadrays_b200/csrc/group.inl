@@ -71,6 +71,7 @@ struct crt_group {
   uint32_t seen_w = 0, seen_h = 0;
   uint64_t first_sample = 0, next_sample = 0;   // the group's sample cursor
   std::vector<cudaEvent_t> done;         // per member: its share of the last crt_group_render has finished
+  std::vector<cudaEvent_t> ev_wave, ev_estimate;   // adaptive sampling: the member's wave is resolved / its tiles' estimates are written
   double last_reduce_ms = 0.0;           // device time of the last exchange + Display pass (slowest member)
   std::vector<cudaEvent_t> t0, t1;
 };
@@ -203,6 +204,64 @@ int group_display(crt_group* g, uint8_t* rgb8, size_t stride8, float* rgbf, size
   return CRT_OK;
 }
 
+// Adaptive screen sampling over the members (AdaptiveScreenSampling with several GPUs behind one Redraw).  Every
+// member holds the same per-tile state and runs the same allocation; of a tile's new samples -- global sample indices
+// count .. count + k - 1 of every pixel of the tile -- member r renders the ones congruent to r modulo N, so the union
+// is the sample set one GPU would render for the same allocation.  After each wave the members exchange: member r
+// rebuilds the error estimate and count of the tiles j = r (mod N) from all members' sums over peer addresses and
+// writes them into every member's arrays (k_adaptive_error_peers); the next wave's allocation waits for that.  All
+// waves of a call are enqueued from this one thread without a host synchronisation, ordered by events.
+int group_render_adaptive(crt_group* g, uint32_t n_samples)
+{
+  const int n = (int)g->members.size();
+  if (!g->peer_ok) return fail(CRT_ERR_STATE, "adaptive screen sampling over a group needs peer access between its GPUs");
+  std::vector<AdaptiveState> A(n);
+  AdaptivePlan plan{};
+  int rc = CRT_OK;
+  for (int r = 0; r < n; ++r) {
+    crt_context* c = g->members[r];
+    if ((rc = render_prepare(c))) return rc;
+    if ((rc = adaptive_begin(c, n_samples, (uint32_t)r, (uint32_t)n, &A[r], &plan))) return rc;
+  }
+  PeerAdaptive G;
+  G.n = n;
+  for (int r = 0; r < n; ++r) {
+    G.accum[r] = g->members[r]->accum; G.even[r] = g->members[r]->ad_even.p;
+    G.err[r] = g->members[r]->ad_err.p; G.count[r] = g->members[r]->ad_count.p;
+  }
+  const uint64_t cap = plan.wave_cap * (uint64_t)n;
+  for (uint64_t left = plan.per_unit * n_samples; left > 0;) {
+    const uint32_t budget = (uint32_t)std::min<uint64_t>(left, cap);
+    for (int r = 0; r < n; ++r) {            // the wave: allocation (from the estimates every member wrote), trace, resolve
+      crt_context* c = g->members[r];
+      if ((rc = set_device(c))) return rc;
+      for (int m = 0; m < n; ++m) CRT_CUDA(cudaStreamWaitEvent(c->stream, g->ev_estimate[m], 0));   // no-op before the first record
+      if ((rc = adaptive_wave(c, A[r], budget))) return rc;
+      CRT_CUDA(cudaEventRecord(g->ev_wave[r], c->stream));
+    }
+    for (int r = 0; r < n; ++r) {            // the exchange: estimates of the tiles j = r (mod n) from all members' sums
+      crt_context* c = g->members[r];
+      if ((rc = set_device(c))) return rc;
+      for (int m = 0; m < n; ++m) CRT_CUDA(cudaStreamWaitEvent(c->stream, g->ev_wave[m], 0));
+      {
+        SpanGuard sg(c, F_RESOLVE);
+        k_adaptive_error_peers<<<grid_for(c, 4), 256, 0, c->stream>>>(G, c->dp, A[r]);
+      }
+      CRT_CUDA(cudaGetLastError());
+      CRT_CUDA(cudaEventRecord(g->ev_estimate[r], c->stream));
+    }
+    left -= budget;
+  }
+  // a later call on any member (reads, the next Redraw) must see every member's estimates
+  for (int r = 0; r < n; ++r) {
+    crt_context* c = g->members[r];
+    if ((rc = set_device(c))) return rc;
+    for (int m = 0; m < n; ++m) CRT_CUDA(cudaStreamWaitEvent(c->stream, g->ev_estimate[m], 0));
+    c->next_sample += n_samples;
+  }
+  return CRT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -253,9 +312,12 @@ int crt_group_create(crt_context* primary, const int* devices, int n_devices, cr
     if (e) { g->comms.clear(); const std::string m = g->nccl.GetErrorString(e); crt_group_destroy(g); return fail(CRT_ERR_CUDA, "ncclCommInitAll: " + m); }
   }
   g->done.assign(n_devices, nullptr); g->t0.assign(n_devices, nullptr); g->t1.assign(n_devices, nullptr);
+  g->ev_wave.assign(n_devices, nullptr); g->ev_estimate.assign(n_devices, nullptr);
   for (int r = 0; r < n_devices; ++r) {
     cudaSetDevice(g->members[r]->device);
     cudaEventCreateWithFlags(&g->done[r], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_wave[r], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_estimate[r], cudaEventDisableTiming);
     cudaEventCreate(&g->t0[r]);
     cudaEventCreate(&g->t1[r]);
   }
@@ -272,6 +334,8 @@ void crt_group_destroy(crt_group* g)
   for (size_t r = 0; r < g->members.size(); ++r) {
     cudaSetDevice(g->members[r]->device);
     if (r < g->done.size() && g->done[r]) cudaEventDestroy(g->done[r]);
+    if (r < g->ev_wave.size() && g->ev_wave[r]) cudaEventDestroy(g->ev_wave[r]);
+    if (r < g->ev_estimate.size() && g->ev_estimate[r]) cudaEventDestroy(g->ev_estimate[r]);
     if (r < g->t0.size() && g->t0[r]) cudaEventDestroy(g->t0[r]);
     if (r < g->t1.size() && g->t1[r]) cudaEventDestroy(g->t1[r]);
   }
@@ -350,12 +414,12 @@ int crt_group_render(crt_group* g, uint32_t n_samples, uint64_t* out_total)
   CRT_REQUIRE(g, "null group");
   crt_context* c0 = g->members[0];
   if (c0->geometry_dirty || g->seen_scene != c0->gen_scene) return fail(CRT_ERR_STATE, "crt_group_render before crt_group_commit");
-  if (c0->params.adaptive_sampling) return fail(CRT_ERR_STATE, "adaptive screen sampling is scheduled per context; render the group with it off");
   int rc = replicate_state(g);
   if (rc) return rc;
   const int n = (int)g->members.size();
   const uint64_t start = g->next_sample;
-  rc = for_each_member(g, [&](int r) -> int {
+  if (c0->params.adaptive_sampling && n > 1) rc = group_render_adaptive(g, n_samples);
+  else rc = for_each_member(g, [&](int r) -> int {
     // contiguous blocks, the first (n_samples mod n) members take one sample more (distributed.sample_range)
     const uint32_t base = n_samples / n, extra = n_samples % n;
     const uint32_t cnt = base + ((uint32_t)r < extra ? 1u : 0u);

@@ -1642,7 +1642,16 @@ struct AdaptiveState {
   float* even;          // per pixel: luminance sum of the even-numbered samples
   uint32_t ntx, nty, nt;
   uint32_t first_parity;  // parity of the first sample index of the accumulation
+  // Several GPUs on one accumulation (crt_group): every member holds the same count / err arrays and runs the same
+  // allocation; of the k new samples of a tile -- global sample indices count .. count + k - 1 -- member `rank` renders
+  // the ones congruent to rank modulo n_members.  cum_own is the exclusive prefix of this member's tile samples
+  // (== cum for one member); the error estimate is then rebuilt from all members' sums by k_adaptive_error_peers.
+  uint32_t* cum_own;
+  uint32_t rank, n_members;
 };
+
+// number of sample indices g in [0, x) with g = rank (mod n)
+__device__ __forceinline__ uint32_t adaptive_own_below(uint32_t x, uint32_t rank, uint32_t n) { return (x + n - 1u - rank) / n; }
 
 __device__ __forceinline__ uint32_t adaptive_valid(const AdaptiveState& A, const DeviceParams& P, uint32_t j, uint32_t& vw, uint32_t& vh)
 {
@@ -1696,17 +1705,34 @@ k_adaptive_allocate(AdaptiveState A, DeviceParams P, uint32_t budget, uint32_t w
   unsigned long long C = block_scan_u64(part, smem, Wt);
   const unsigned long long off = ((unsigned long long)((wave * 40503u) & 0xffffu) * Wt) >> 16;
   // tile samples and paths of this thread's run
-  unsigned long long paths = 0;
+  unsigned long long paths = 0, own = 0;
   {
     unsigned long long c = C;
     for (uint32_t j = j0; j < j1; ++j) {
       const unsigned long long w = min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
       const uint32_t a = (uint32_t)((c * budget + off) / Wt), b = (uint32_t)(((c + w) * budget + off) / Wt);
       uint32_t vw, vh;
-      paths += (unsigned long long)(b - a) * adaptive_valid(A, P, j, vw, vh);
+      const uint32_t cj = A.count[j];
+      const uint32_t mine = adaptive_own_below(cj + (b - a), A.rank, A.n_members) - adaptive_own_below(cj, A.rank, A.n_members);
+      paths += (unsigned long long)mine * adaptive_valid(A, P, j, vw, vh);
+      own += mine;
       A.cum[j] = a;
       c += w;
     }
+  }
+  if (A.n_members > 1) {                         // prefix of this member's tile samples (one member: cum_own aliases cum)
+    unsigned long long own_total = 0;
+    unsigned long long o = block_scan_u64(own, smem, own_total);
+    unsigned long long c = C;
+    for (uint32_t j = j0; j < j1; ++j) {
+      const unsigned long long w = min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
+      const uint32_t a = (uint32_t)((c * budget + off) / Wt), b = (uint32_t)(((c + w) * budget + off) / Wt);
+      const uint32_t cj = A.count[j];
+      A.cum_own[j] = (uint32_t)o;
+      o += adaptive_own_below(cj + (b - a), A.rank, A.n_members) - adaptive_own_below(cj, A.rank, A.n_members);
+      c += w;
+    }
+    if (threadIdx.x == 0) A.cum_own[A.nt] = (uint32_t)own_total;
   }
   unsigned long long total_paths = 0;
   unsigned long long q = block_scan_u64(paths, smem, total_paths);
@@ -1716,8 +1742,10 @@ k_adaptive_allocate(AdaptiveState A, DeviceParams P, uint32_t budget, uint32_t w
       const unsigned long long w = min(max((unsigned long long)A.err[j], lo), hi) + 1ull;
       const uint32_t a = (uint32_t)((c * budget + off) / Wt), b = (uint32_t)(((c + w) * budget + off) / Wt);
       uint32_t vw, vh;
+      const uint32_t cj = A.count[j];
       A.qoff[j] = (uint32_t)q;
-      q += (unsigned long long)(b - a) * adaptive_valid(A, P, j, vw, vh);
+      q += (unsigned long long)(adaptive_own_below(cj + (b - a), A.rank, A.n_members) - adaptive_own_below(cj, A.rank, A.n_members))
+           * adaptive_valid(A, P, j, vw, vh);
       c += w;
     }
   }
@@ -1729,16 +1757,19 @@ k_adaptive_allocate(AdaptiveState A, DeviceParams P, uint32_t budget, uint32_t w
 __global__ void __launch_bounds__(256)
 k_generate_adaptive(PathState st, DeviceParams P, AdaptiveState A, const uint32_t* __restrict__ seeds, uint32_t budget)
 {
-  const uint32_t total = budget * kAdaptiveSlots;
+  (void)budget;
+  const uint32_t total = A.cum_own[A.nt] * kAdaptiveSlots;      // this member's tile samples (one member: the budget)
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += stride) {
     const uint32_t ts = slot >> 10, within = slot & 1023u;
-    uint32_t lo = 0, hi = A.nt;                 // last j with cum[j] <= ts  (warp-uniform search)
+    uint32_t lo = 0, hi = A.nt;                 // last j with cum_own[j] <= ts  (warp-uniform search)
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(A.cum + mid) <= ts) lo = mid; else hi = mid;
+      if (__ldg(A.cum_own + mid) <= ts) lo = mid; else hi = mid;
     }
-    const uint32_t j = lo, t = ts - __ldg(A.cum + j);
+    const uint32_t j = lo, tl = ts - __ldg(A.cum_own + j);
+    // the tl-th sample of this member in the tile: global index count + t with (count + t) = rank (mod n_members)
+    const uint32_t t = (A.rank + A.n_members - __ldg(A.count + j) % A.n_members) % A.n_members + tl * A.n_members;
     const uint32_t sub = within >> 5, lane = within & 31u;
     const uint32_t lx = (sub & 3u) * 8u + (lane & 7u), ly = (sub >> 2) * 4u + (lane >> 3);
     uint32_t vw, vh;
@@ -1747,7 +1778,7 @@ k_generate_adaptive(PathState st, DeviceParams P, AdaptiveState A, const uint32_
       const uint32_t px = (j % A.ntx) * kAdaptiveTile + lx, py = (j / A.ntx) * kAdaptiveTile + ly;
       generate_path(st, P, slot, px, py, __ldg(seeds + __ldg(A.count + j) + t));
       const uint32_t pos = (nv == kAdaptiveSlots) ? within : ly * vw + lx;
-      st.queue[0][__ldg(A.qoff + j) + t * nv + pos] = slot;
+      st.queue[0][__ldg(A.qoff + j) + tl * nv + pos] = slot;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) st.n_active[0] = A.qoff[A.nt];
@@ -1765,9 +1796,11 @@ k_resolve_adaptive(PathState st, DeviceParams P, AdaptiveState A, float4* __rest
 {
   __shared__ uint32_t s_err[8];
   for (uint32_t j = blockIdx.x; j < A.nt; j += gridDim.x) {
-    const uint32_t c0 = A.cum[j], k = A.cum[j + 1] - c0;
+    const uint32_t c0 = A.cum_own[j], k = A.cum_own[j + 1] - c0;      // this member's new samples of the tile
     if (k == 0) continue;                        // block-uniform
+    const bool alone = A.n_members == 1u;        // several members: err / count are rebuilt from all sums afterwards
     const uint32_t n_old = A.count[j], n_new = n_old + k;
+    const uint32_t t_first = (A.rank + A.n_members - n_old % A.n_members) % A.n_members;
     const uint32_t n_even = A.first_parity ? n_new / 2u : (n_new + 1u) / 2u;
     uint32_t vw, vh;
     const uint32_t nv = adaptive_valid(A, P, j, vw, vh);
@@ -1786,11 +1819,11 @@ k_resolve_adaptive(PathState st, DeviceParams P, AdaptiveState A, float4* __rest
         const float g = (c.y != c.y) ? 0.0f : minf(c.y, P.max_radiance);
         const float b = (c.z != c.z) ? 0.0f : minf(c.z, P.max_radiance);
         a.x += r; a.y += g; a.z += b; a.w += 1.0f;
-        if (((A.first_parity + n_old + t) & 1u) == 0u) ev += luminance(r, g, b);
+        if (((A.first_parity + n_old + t_first + t * A.n_members) & 1u) == 0u) ev += luminance(r, g, b);
       }
       accum[pix] = a;
       A.even[pix] = ev;
-      if (n_new >= 2u && n_even > 0u) {
+      if (alone && n_new >= 2u && n_even > 0u) {
         const float l_all = luminance(a.x, a.y, a.z) / (float)n_new;
         const float l_even = ev / (float)n_even;
         const float e = fabsf(sqrtf(minf(maxf(l_all, 0.0f), 1.0f)) - sqrtf(minf(maxf(l_even, 0.0f), 1.0f)));
@@ -1805,9 +1838,65 @@ k_resolve_adaptive(PathState st, DeviceParams P, AdaptiveState A, float4* __rest
     if (threadIdx.x == 0) {
       uint32_t e = 0;
       for (int w = 0; w < 8; ++w) e += s_err[w];
-      A.err[j] = e;
-      A.count[j] = n_new;
+      if (alone) { A.err[j] = e; A.count[j] = n_new; }
       if (gcnt) atomicAdd(&gcnt->samples, (unsigned long long)nv * k);
+    }
+  }
+}
+
+// Adaptive sampling over several GPUs (crt_group), the exchange step of a wave: member `rank` rebuilds the error
+// estimate and the sample count of the tiles j = rank (mod n) from ALL members' sums -- the float4 accumulation
+// buffers and the even-sample planes, read through peer addresses and added in member order -- and writes the two
+// numbers into every member's arrays, so that all members run the next allocation from the same global estimate.
+constexpr int kMaxGroupAdaptive = 16;
+struct PeerAdaptive {
+  const float4* accum[kMaxGroupAdaptive];
+  const float* even[kMaxGroupAdaptive];
+  uint32_t* err[kMaxGroupAdaptive];
+  uint32_t* count[kMaxGroupAdaptive];
+  int n;
+};
+
+__global__ void __launch_bounds__(256)
+k_adaptive_error_peers(PeerAdaptive G, DeviceParams P, AdaptiveState A)
+{
+  __shared__ uint32_t s_err[8];
+  for (uint32_t j = A.rank + blockIdx.x * A.n_members; j < A.nt; j += gridDim.x * A.n_members) {
+    const uint32_t k = A.cum[j + 1] - A.cum[j];  // new samples of the tile in this wave, over all members
+    if (k == 0) continue;                        // block-uniform
+    const uint32_t n_new = A.count[j] + k;
+    const uint32_t n_even = A.first_parity ? n_new / 2u : (n_new + 1u) / 2u;
+    uint32_t vw, vh;
+    adaptive_valid(A, P, j, vw, vh);
+    uint32_t e_sum = 0;
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t q = threadIdx.x + 256u * i;
+      const uint32_t lx = q & 31u, ly = q >> 5;
+      if (lx >= vw || ly >= vh) continue;
+      const size_t pix = (size_t)((j / A.ntx) * kAdaptiveTile + ly) * P.width + (j % A.ntx) * kAdaptiveTile + lx;
+      float4 a = G.accum[0][pix];
+      float ev = G.even[0][pix];
+      for (int m = 1; m < G.n; ++m) {
+        const float4 b = G.accum[m][pix];
+        a.x += b.x; a.y += b.y; a.z += b.z;
+        ev += G.even[m][pix];
+      }
+      if (n_new >= 2u && n_even > 0u) {
+        const float l_all = luminance(a.x, a.y, a.z) / (float)n_new;
+        const float l_even = ev / (float)n_even;
+        const float e = fabsf(sqrtf(minf(maxf(l_all, 0.0f), 1.0f)) - sqrtf(minf(maxf(l_even, 0.0f), 1.0f)));
+        e_sum += (uint32_t)(e * 4096.0f);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+    __syncthreads();                             // s_err free again
+    if ((threadIdx.x & 31u) == 0u) s_err[threadIdx.x >> 5] = e_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t e = 0;
+      for (int w = 0; w < 8; ++w) e += s_err[w];
+      for (int m = 0; m < G.n; ++m) { G.err[m][j] = e; G.count[m][j] = n_new; }
     }
   }
 }

@@ -30,6 +30,17 @@ def step_sample_start(step: int, rank: int, world: int, spp_per_step: int) -> in
     return (step * world + rank) * spp_per_step
 
 
+def adaptive_tile_share(count: int, k: int, rank: int, world: int):
+    """Adaptive screen sampling over several GPUs (csrc/group.inl, k_adaptive_allocate): a tile whose pixels hold
+    `count` samples receives `k` more -- global sample indices count .. count + k - 1 -- and member `rank` of `world`
+    renders the ones congruent to its rank.  Returns (first local offset t0, number of own samples): the member's
+    samples are count + t0 + i * world for i < number.  The same integers the kernels compute."""
+    if not (0 <= rank < world) or count < 0 or k < 0:
+        raise ValueError("bad rank/world/count")
+    below = lambda x: (x + world - 1 - rank) // world          # sample indices < x congruent to rank
+    return (rank + world - count % world) % world, below(count + k) - below(count)
+
+
 def init_from_env(backend: str | None = None):
     """torch.distributed bootstrap from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*."""
     import torch

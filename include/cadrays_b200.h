@@ -300,8 +300,10 @@ int crt_read_ldr_from(crt_context* ctx, const void* device_accum, uint8_t* rgb8,
  *                        0 + the ordinary Display pass (libnccl.so.2 is bound with dlopen at group creation).
  * Setters are called on `primary` only; every crt_group_* call replicates what changed since the last one
  * (a camera or parameter change restarts the accumulation on all members, as on one context).  Do not call
- * crt_render / crt_commit on the primary directly while it belongs to a group.  Adaptive screen sampling
- * is per context and is refused by crt_group_render. */
+ * crt_render / crt_commit on the primary directly while it belongs to a group.  With adaptive screen sampling
+ * (crt_params.adaptive_sampling) every member runs the same tile allocation from the same global error estimate and
+ * renders the tile samples whose global sample index is congruent to its rank modulo the member count; after each
+ * wave the members rebuild the estimate from all members' sums over peer addresses (needs peer access). */
 typedef struct crt_group crt_group;
 int  crt_group_create(crt_context* primary, const int* devices, int n_devices, crt_group** out_group);
 void crt_group_destroy(crt_group* group);            /* destroys the replicas; `primary` stays with the caller */

@@ -113,3 +113,25 @@ def test_sample_partition_properties_randomised():
 
     ranges()
     schedule()
+
+
+def test_adaptive_tile_share_partitions_every_tile():
+    """The dealing rule of adaptive sampling over a group: for any tile state the members' shares are disjoint, cover
+    the tile's new samples exactly, differ in size by at most one, and follow on from wave to wave."""
+    import random
+    rnd = random.Random(3)
+    for _ in range(3000):
+        world = rnd.randint(1, 9)
+        count, k = rnd.randint(0, 60), rnd.randint(0, 40)
+        seen = []
+        sizes = []
+        for r in range(world):
+            t0, n = D.adaptive_tile_share(count, k, r, world)
+            own = [count + t0 + i * world for i in range(n)]
+            assert all(count <= g < count + k and g % world == r for g in own)
+            seen += own
+            sizes.append(n)
+        assert sorted(seen) == list(range(count, count + k))
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        D.adaptive_tile_share(0, 1, 2, 2)

@@ -192,3 +192,57 @@ def test_group_nccl_path(product_lib):
     env = dict(os.environ, CRT_GROUP_REDUCE="nccl", PYTHONPATH=str(REPO))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_group_adaptive_sampling(product_lib):
+    """AdaptiveScreenSampling behind a group: every member schedules from the same global estimate and renders the
+    tile samples whose global index is congruent to its rank, so (1) the budget is spent exactly and unevenly, (2) a
+    pixel whose tile received n samples holds the first n samples of its plain stream -- the combined frame equals a
+    plain n-spp render of that pixel up to float summation order -- and (3) one member behaves exactly as a plain
+    context does."""
+    desc = scenes.assembly(n_parts=64, target_tris=40_000, seed=2, width=256, height=160, depth=6)
+    p = desc.params
+    p.AdaptiveScreenSampling, p.NbRayTracingTiles, p.SamplesPerBatch = True, 0, 2
+    single = V3d_View(0)
+    desc.apply(single)
+    single.Redraw(3); single.Redraw(5)         # the same calls as the groups below: the waves depend on them
+    ref_counts, _ = single.SamplingTiles()
+    ref_hdr = single.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+    single.Remove()
+    assert int(ref_counts.sum()) == 8 * ref_counts.size and ref_counts.max() > ref_counts.min()
+
+    plain = V3d_View(0)
+    pp = scenes.assembly(n_parts=64, target_tris=40_000, seed=2, width=256, height=160, depth=6)
+    pp.apply(plain)
+    plain_hdr = {}
+
+    def plain_at(n):                       # plain render of the first n samples of every pixel (every n up to it is cached)
+        while (max(plain_hdr) if plain_hdr else 0) < n:
+            plain.Redraw(1)
+            plain_hdr[(max(plain_hdr) if plain_hdr else 0) + 1] = plain.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+        return plain_hdr[n]
+
+    for devices in _device_lists():
+        view = V3d_View(devices=devices)
+        desc.apply(view)
+        assert view.Redraw(3) == 3 and view.Redraw(5) == 8          # two calls, several waves each
+        counts, errs = view.SamplingTiles()
+        hdr = view.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+        view.Remove()
+        assert int(counts.sum()) == 8 * counts.size, devices
+        assert counts.max() > counts.min() and counts.min() >= 1, devices
+        if len(devices) == 1:
+            assert np.array_equal(counts, ref_counts) and np.array_equal(hdr, ref_hdr)
+        else:
+            # a group's wave holds N times the tile samples of a single context's, so the allocation is not the same
+            # sequence of decisions -- but it follows the same estimate: the busy tiles are the same ones
+            assert np.corrcoef(counts.ravel().astype(np.float64), ref_counts.ravel().astype(np.float64))[0, 1] > 0.8, devices
+        # BufferDump rows are bottom-up, as the accumulation buffer's rows are: tile row 0 is image row 0 of the dump
+        per_pixel = np.repeat(np.repeat(counts, 32, axis=0), 32, axis=1)[:desc.height, :desc.width]
+        checked = 0
+        for n in sorted(np.unique(counts)):
+            m = per_pixel == n
+            assert _rel(hdr[m], plain_at(int(n))[m]) <= GROUP_TOL, (devices, int(n), _rel(hdr[m], plain_at(int(n))[m]))
+            checked += int(m.sum())
+        assert checked == desc.width * desc.height
+    plain.Remove()
