@@ -166,6 +166,68 @@ def simulate(events, strategy, threshold=1):
     return total_issue, useful
 
 
+def simulate_phase_pool(events, pool_size=64, gather=40, exit_lanes=12, leaf_pairs=True):
+    """A warp owns `pool_size` rays whose state lives in shared memory; it repeatedly picks up to 32 rays that are in the
+    same phase (node walk / leaf / instance switch), gathers them into registers (`gather` instructions each way), and
+    runs that phase with (nearly) full lanes; the node phase is left once fewer than `exit_lanes` lanes still walk.
+    Leaf phase: one (ray, triangle) pair per lane and round when leaf_pairs, else one leaf per lane.  Returns
+    (warp instruction issues, useful lane instructions) like simulate()."""
+    n = len(events)
+    useful = 0
+    for e in events:
+        for c in e:
+            useful += C_N if c == 1 else (C_S if c == 2 else C_L0 + C_T * (c - 3))
+    total = 0
+    chunk = pool_size * 48
+    for base in range(0, n, chunk):
+        queue = list(range(base, min(base + chunk, n)))
+        queue.reverse()
+        pool = []                    # [events, index]
+        while True:
+            pool = [r for r in pool if r[1] < len(r[0])]
+            if len(pool) < pool_size and queue:
+                total += C_R
+                while len(pool) < pool_size and queue:
+                    pool.append([events[queue.pop()], 0])
+                pool = [r for r in pool if r[1] < len(r[0])]
+            if not pool:
+                if not queue:
+                    break
+                continue
+            walk = [r for r in pool if r[0][r[1]] == 1]
+            sw = [r for r in pool if r[0][r[1]] == 2]
+            leaf = [r for r in pool if r[0][r[1]] >= 3]
+            # pick the phase with the most waiting rays (ties: walk)
+            if len(walk) >= max(len(sw), len(leaf)) and walk:
+                sel = walk[:32]
+                total += 2 * gather
+                first = True
+                while True:
+                    act = [r for r in sel if r[1] < len(r[0]) and r[0][r[1]] == 1]
+                    if not act or (not first and len(act) < exit_lanes and len(pool) > len(sel)):
+                        break
+                    first = False
+                    total += C_N
+                    for r in act:
+                        r[1] += 1
+            elif len(leaf) >= len(sw) and leaf:
+                sel = leaf[:32]
+                total += 2 * gather
+                if leaf_pairs:
+                    pairs = sum(r[0][r[1]] - 3 for r in sel)
+                    total += C_L0 + (C_T + 10) * max(1, (pairs + 31) // 32)
+                else:
+                    total += C_L0 + C_T * max(r[0][r[1]] - 3 for r in sel)
+                for r in sel:
+                    r[1] += 1
+            else:
+                sel = sw[:32]
+                total += 2 * gather + C_S
+                for r in sel:
+                    r[1] += 1
+    return total, useful
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=32768)
@@ -181,6 +243,9 @@ def main():
         for strat, thr in (("while-while", 1), ("while-while", 12), ("while-while", 20), ("inloop-switch", 1), ("if-if", 1), ("tri-step", 1)):
             issue, useful = simulate(ev, strat, thr)
             print(f"   {strat:14s} thr={thr:2d}: warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
+        for ps, g, ex in ((64, 40, 12), (64, 40, 20), (96, 40, 16), (128, 40, 16), (64, 70, 16), (64, 20, 16)):
+            issue, useful = simulate_phase_pool(ev, ps, g, ex)
+            print(f"   phase-pool {ps:3d} rays, gather {g}, exit<{ex}: warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
         # sorted variant: group rays by origin cell + direction octant before forming warps
         lo, hi = o.min(0), o.max(0)
         cell = np.clip(((o - lo) / np.maximum(hi - lo, 1e-9) * 16).astype(int), 0, 15)
