@@ -1401,7 +1401,7 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
     uint32_t rng = 0;
     bool inside = false;
     if (valid) {
-      float4 hh, rr;
+      float4 hh;
       if (FIRST) {
         // depth 0 after k_extend_primary: slot i is pixel sample i; its state is (camera ray, throughput 1, radiance 0)
         slot = i;
@@ -1410,24 +1410,28 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
         const uint32_t tile = P.tile0 + (in >> 5), ln = in & 31u;
         camera_ray(P, (tile % P.tiles_x) * 8u + (ln & 7u), (tile / P.tiles_x) * 4u + (ln >> 3), __ldg(seeds + k), org, dir, rng);
         thr = V(1.0f, 1.0f, 1.0f);
-        rr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         hh = ld_stream(&st.hit[slot]);
       } else {
         if (!SORT) slot = ld_stream(&q[i]);
         const float4 ro = ld_stream(&st.ray_o[slot]), rd = ld_stream(&st.ray_d[slot]), tw = ld_stream(&st.thr[slot]);
         hh = ld_stream(&st.hit[slot]);
-        rr = ld_stream(&st.rad[slot]);
         org = V(ro.x, ro.y, ro.z); dir = V(rd.x, rd.y, rd.z);
         imp_pdf = ro.w;
         inside = (__float_as_int(rd.w) & 1) != 0;
         thr = V(tw.x, tw.y, tw.z);
         rng = __float_as_uint(tw.w);
       }
-      v3 radiance = V(rr.x, rr.y, rr.z);
+      // A bounce adds to the path's radiance at most once (a light / environment hit or the surface's emission), and
+      // for most paths it adds nothing: the bounce is shaded against a zero, and the 16-byte radiance record is read
+      // and rewritten only when there is something to add (x + 0 == x bit for bit, so skipping the add changes nothing).
+      v3 radiance = V(0.0f, 0.0f, 0.0f);
       shade_bounce<COUNT, TEX, LEAN>(S, P, depth, two_sided, eps, hh, &st.hit_inst[slot], -1, org, dir, thr, imp_pdf, rng, inside, radiance,
                                      want_shadow, sh_o, sh_d, sh_c, sh_tmax, want_next, cnt, smem_mats);
-      if (FIRST || radiance.x != rr.x || radiance.y != rr.y || radiance.z != rr.z) {   // FIRST: this write initialises the slot
-        rr.x = radiance.x; rr.y = radiance.y; rr.z = radiance.z;
+      if (FIRST) {                               // this write initialises the slot
+        st_stream(&st.rad[slot], make_float4(radiance.x, radiance.y, radiance.z, 0.0f));
+      } else if (radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f) {     // also true for NaN
+        float4 rr = ld_stream(&st.rad[slot]);
+        rr.x += radiance.x; rr.y += radiance.y; rr.z += radiance.z;
         st_stream(&st.rad[slot], rr);
       }
     }
