@@ -316,8 +316,13 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_CHUNK
 #define CRT_CHUNK 64
 #endif
+// Lanes leave the loop that walks inner nodes once fewer than CRT_INNER_EXIT lanes of the warp are still walking while
+// another lane waits for its leaf / instance step (1 = walk until every lane is done).  With OCCT's leaves of 5
+// triangles this lost (round 1: +-0 ... -10 %); with leaves of 2 the step the waiting lanes get to sooner is short, and
+// it pays: lanes per instruction 10.1 -> 13.6, warp instructions -20 %, traversal 17.9 -> 16.5 ms per step together
+// with 8 instead of 9 resident CTAs (N = 4 / 6 / 8 / 10 / 12 / 16: 17.19 / 17.00 / 16.95 / 17.00 / 17.19 / 17.81 ms at 9 CTAs).
 #ifndef CRT_INNER_EXIT
-#define CRT_INNER_EXIT 1
+#define CRT_INNER_EXIT 8
 #endif
 #ifndef CRT_PREFETCH
 #define CRT_PREFETCH 0
@@ -325,11 +330,13 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_SMEM_TOP
 #define CRT_SMEM_TOP 0
 #endif
-// Resident CTAs per SM the traversal kernels are compiled for.  Measured on the B200 (ms of traversal per step, C2 /
-// C5 flattened): 7 CTAs (72 registers) 20.33 / 29.64, 8 (64) 19.78 / 28.02, 9 (56) 19.64 / 27.20, 10 (48) 20.29 / 27.61,
-// 12 (40) 21.28 / 27.82 -- more warps hide the dependent node loads until spills take over.
+// Resident CTAs per SM the traversal kernels are compiled for.  Round 1 (ms of traversal per step, C2 / C5 flattened):
+// 7 CTAs (72 registers) 20.33 / 29.64, 8 (64) 19.78 / 28.02, 9 (56) 19.64 / 27.20, 10 (48) 20.29 / 27.61, 12 (40)
+// 21.28 / 27.82.  With the node-loop exit threshold the walk issues 20 % fewer instructions and leans on the L1 data
+// pipe instead (84 % busy); the spills of the 56-register build then cost more than the ninth CTA hides:
+// 7 / 8 / 9 / 10 CTAs: 17.14 / 16.47 / 16.95 / 17.41 ms (C2).
 #ifndef CRT_TRACE_MIN_BLOCKS
-#define CRT_TRACE_MIN_BLOCKS 9
+#define CRT_TRACE_MIN_BLOCKS 8
 #endif
 constexpr uint32_t kChunk = CRT_CHUNK;
 

@@ -228,6 +228,67 @@ def simulate_phase_pool(events, pool_size=64, gather=40, exit_lanes=12, leaf_pai
     return total, useful
 
 
+def simulate_lane_smt(events, k=2, gather=40, exit_lanes=12):
+    """Every lane owns k rays (state outside the registers, stacks stay thread-local); the warp votes for a phase and each
+    lane works on one of ITS rays that is in that phase, if it has one.  No ray ever changes lanes."""
+    n = len(events)
+    useful = 0
+    for e in events:
+        for c in e:
+            useful += C_N if c == 1 else (C_S if c == 2 else C_L0 + C_T * (c - 3))
+    total = 0
+    chunk = 32 * k * 24
+    for base in range(0, n, chunk):
+        queue = list(range(base, min(base + chunk, n)))
+        queue.reverse()
+        lanes = [[None] * k for _ in range(32)]
+        def phase(r):
+            if r is None or r[1] >= len(r[0]): return 0
+            c = r[0][r[1]]
+            return 1 if c == 1 else (2 if c == 2 else 3)
+        while True:
+            refilled = False
+            for l in range(32):
+                for j in range(k):
+                    if phase(lanes[l][j]) == 0:
+                        lanes[l][j] = None
+                        if queue:
+                            lanes[l][j] = [events[queue.pop()], 0]; refilled = True
+            if refilled:
+                total += C_R
+            counts = [0, 0, 0, 0]
+            for l in range(32):
+                ps = {phase(r) for r in lanes[l]}
+                for p in (1, 2, 3):
+                    if p in ps: counts[p] += 1
+            if sum(counts) == 0:
+                if not queue: break
+                continue
+            p = max((1, 3, 2), key=lambda x: counts[x])
+            sel = []
+            for l in range(32):
+                for r in lanes[l]:
+                    if phase(r) == p:
+                        sel.append(r); break
+            total += 2 * gather
+            if p == 1:
+                first = True
+                while True:
+                    act = [r for r in sel if phase(r) == 1]
+                    if not act or (not first and len(act) < exit_lanes):
+                        break
+                    first = False
+                    total += C_N
+                    for r in act: r[1] += 1
+            elif p == 3:
+                total += C_L0 + C_T * max(r[0][r[1]] - 3 for r in sel)
+                for r in sel: r[1] += 1
+            else:
+                total += C_S
+                for r in sel: r[1] += 1
+    return total, useful
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=32768)
@@ -246,6 +307,9 @@ def main():
         for ps, g, ex in ((64, 40, 12), (64, 40, 20), (96, 40, 16), (128, 40, 16), (64, 70, 16), (64, 20, 16)):
             issue, useful = simulate_phase_pool(ev, ps, g, ex)
             print(f"   phase-pool {ps:3d} rays, gather {g}, exit<{ex}: warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
+        for k, g, ex in ((2, 40, 12), (2, 40, 20), (3, 40, 16), (4, 40, 16), (2, 25, 16), (2, 60, 16)):
+            issue, useful = simulate_lane_smt(ev, k, g, ex)
+            print(f"   lane-smt {k} rays per lane, gather {g}, exit<{ex}: warp issues {issue/len(ev):8.1f} per ray, lane efficiency {useful / (32 * issue):.3f}")
         # sorted variant: group rays by origin cell + direction octant before forming warps
         lo, hi = o.min(0), o.max(0)
         cell = np.clip(((o - lo) / np.maximum(hi - lo, 1e-9) * 16).astype(int), 0, 15)
