@@ -251,15 +251,17 @@ def build_roofline(workload, stats, timing, steps, scene_bytes, clocks, probe_de
              "issue_active_pct": ent.get("issue_active_pct"), "lanes_per_inst": ent.get("lanes_per_inst"),
              "l1_data_pipe_pct": ent.get("l1_data_pipe_pct")}
     # ---- which unit binds: the one the ncu counters of the committed capture show nearest its limit
-    util = {"issue": ent.get("issue_active_pct"), "l1": ent.get("l1_data_pipe_pct"),
-            "l2": (100.0 * l2["frac"]) if l2 and l2.get("frac") and l2.get("l2_resident") else ent.get("l2_pct"),
+    # hardware utilisation of each unit during the traversal launches (ncu, time-weighted over one step; the L2 figure
+    # is lts__throughput -- roofline.l2.frac is a different thing: algorithmic bytes over the measured record bandwidth)
+    util = {"issue": ent.get("issue_active_pct"), "l1": ent.get("l1_data_pipe_pct"), "l2": ent.get("l2_pct"),
             "hbm": (100.0 * hbm["dram_frac"]) if "dram_frac" in hbm else None}
     known = {u: v for u, v in util.items() if isinstance(v, (int, float))}
     bound = max(known, key=known.get) if known else "unknown"
     return {
         "bound": bound, "utilisation_pct": util,
-        "bound_note": "no single unit is saturated: the walk is a chain of dependent loads executed with few useful lanes per warp "
-                      "instruction; `bound` is the unit nearest its limit, hbm/l2/issue give every fraction SURVEY 8(d) asks for",
+        "bound_note": "`bound` is the unit the ncu counters of the committed launch list (profiles/issue_calibration.json) show nearest "
+                      "its limit during the traversal launches: the L1 data pipe (one wavefront per lane and node / triangle / stack "
+                      "access), with issue slots half busy at 14 of 32 lanes; hbm / l2 / issue give every fraction SURVEY 8(d) asks for",
         "kernel": "traversal launches: k_extend_primary + k_trace_dual + k_connect (SceneNearestHit / SceneAnyHit)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": traffic, "traffic_provenance": traffic_prov,

@@ -1090,8 +1090,11 @@ k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __
 // The same for the binary tree in lockstep: a warp takes the 32 slots of one 8x4 pixel tile and walks them together
 // (no per-lane refill).  Camera rays of a tile visit nearly the same nodes, so staying in step keeps most lanes active
 // (the persistent driver mixes rays at different stages in a warp: 14.8 of 32 lanes, issue slots 78 % busy).
+#ifndef CRT_PRIMARY_MIN_BLOCKS
+#define CRT_PRIMARY_MIN_BLOCKS 9      // no per-lane refill state: 56 registers without spills (3.13 ms per step at 9 CTAs, 3.25 at 8)
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_PRIMARY_MIN_BLOCKS)
 k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __restrict__ seeds, uint32_t n_batch, Counters* gcnt)
 {
   const uint32_t per_sample = P.n_tiles * 32u;
