@@ -327,6 +327,12 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, v3 org, v3 dir, f
 #ifndef CRT_PREFETCH
 #define CRT_PREFETCH 0
 #endif
+// Finished lanes of the persistent driver retire and take their next ray together, once CRT_REFILL_MIN of them wait
+// (or no lane of the warp has work left): 1 / 2 / 4 / 8 / 12 / 16 / 24 -> 16.55 / 16.37 / 16.34 / 16.23 / 16.30 / 16.54 /
+// 17.90 ms of traversal per step (C2).
+#ifndef CRT_REFILL_MIN
+#define CRT_REFILL_MIN 8
+#endif
 #ifndef CRT_SMEM_TOP
 #define CRT_SMEM_TOP 0
 #endif
@@ -401,10 +407,17 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
   int32_t inst = -1;
   for (;;) {
     // ---- retire finished rays, hand out new ones
-    if (cur == kDone && has_ray) { pol.store(token, hit, found, any_ray); has_ray = false; }
     const bool need = cur == kDone;
     const unsigned m = __ballot_sync(FULL, need);
-    if (m) {
+#if CRT_REFILL_MIN > 1
+    // finished lanes wait until CRT_REFILL_MIN of them can retire and refill together (or no lane has work left):
+    // fewer, fuller passes through the retire / refill code and its dependent state loads
+    const bool do_refill = m != 0u && ((int)__popc(m) >= CRT_REFILL_MIN || m == FULL);
+#else
+    const bool do_refill = m != 0u;
+#endif
+    if (do_refill && cur == kDone && has_ray) { pol.store(token, hit, found, any_ray); has_ray = false; }
+    if (do_refill) {
       if (pool_next == pool_end && !drained) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(work, chunk);
@@ -432,7 +445,11 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
     }
     const unsigned live = __ballot_sync(FULL, has_ray);
     if (drained && live == 0) break;
+#if CRT_REFILL_MIN > 1
+    const int n_live = __popc(__ballot_sync(FULL, cur != kDone));    // lanes with work (finished lanes may be waiting to retire)
+#else
     const int n_live = __popc(live);
+#endif
 
     // ---- inner nodes.  CRT_INNER_EXIT = N > 1: lanes leave the loop once fewer than N lanes are still
     // walking inner nodes while another lane of the warp waits for its leaf / instance step (the
