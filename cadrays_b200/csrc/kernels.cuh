@@ -634,6 +634,16 @@ __device__ __forceinline__ float fresnel_conductor(float cos_i, float eta, float
 }
 
 // Graphic3d_Fresnel::Serialize() encoding (MaterialEditor.cxx:209-255).
+// conductor / dielectric interfaces out of line (OL: the instantiations of the shading kernels for scenes without coat
+// and transmission -- fresnel_media is inlined at eight places, the two exact models are most of its code and such
+// scenes rarely use them: k_shade -3.7 % on C2; scenes with glass keep them inline, where the call costs 2 %)
+__device__ __noinline__ float fresnel_exact(float cos_i, float fx, float fy, float fz)
+{
+  if (fx > -2.5f) return fresnel_conductor(fabsf(cos_i), fy, fz);
+  return fresnel_dielectric(cos_i, fy);
+}
+
+template <bool OL = false>
 __device__ __forceinline__ v3 fresnel_media(float cos_i, v3 f)
 {
   if (f.x > -0.5f) {
@@ -643,6 +653,7 @@ __device__ __forceinline__ v3 fresnel_media(float cos_i, v3 f)
     return V(f.x + (1.0f - f.x) * m5, f.y + (1.0f - f.y) * m5, f.z + (1.0f - f.z) * m5);
   }
   if (f.x > -1.5f) return V(f.z, f.z, f.z);
+  if (OL) { const float c = fresnel_exact(cos_i, f.x, f.y, f.z); return V(c, c, c); }
   if (f.x > -2.5f) { float c = fresnel_conductor(fabsf(cos_i), f.y, f.z); return V(c, c, c); }
   float c = fresnel_dielectric(cos_i, f.y);
   return V(c, c, c);
@@ -663,13 +674,14 @@ __device__ __forceinline__ float smith_g1(v3 dir, v3 m, float a)
   return 2.0f / (1.0f + sqrtf(fmaf(a * a, tan2, 1.0f)));
 }
 
+template <bool OL = false>
 __device__ __forceinline__ v3 eval_ggx(v3 wi, v3 wo, v3 fresnel, float a)
 {
   if (wi.z <= 0.0f || wo.z <= 0.0f) return V(0, 0, 0);
   v3 h = normalize3(vadd(wi, wo));
   float d = ggx_d(h.z, a);
   float g = smith_g1(wo, h, a) * smith_g1(wi, h, a);
-  return vscale(fresnel_media(dot3(wo, h), fresnel), d * g / (4.0f * wo.z));
+  return vscale(fresnel_media<OL>(dot3(wo, h), fresnel), d * g / (4.0f * wo.z));
 }
 
 __device__ __forceinline__ float eval_lambert(v3 wi, v3 wo)
@@ -677,14 +689,15 @@ __device__ __forceinline__ float eval_lambert(v3 wi, v3 wo)
   return (wi.z <= 0.0f || wo.z <= 0.0f) ? 0.0f : wi.z * CRT_INV_PI;
 }
 
+template <bool OL = false>
 __device__ __forceinline__ v3 eval_bsdf_layered(const Bsdf& b, v3 wi, v3 wo, bool two_sided)
 {
   if (two_sided) { wi.z = fabsf(wi.z); wo.z = fabsf(wo.z); }
   v3 r = vscale(b.Kd, eval_lambert(wi, wo));
-  if (b.Ks_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Ks, eval_ggx(wi, wo, b.Fb, b.Ks_w)));
-  v3 cf = fresnel_media(wo.z, b.Fc);
+  if (b.Ks_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Ks, eval_ggx<OL>(wi, wo, b.Fb, b.Ks_w)));
+  v3 cf = fresnel_media<OL>(wo.z, b.Fc);
   r = vmul(r, V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z));
-  if (b.Kc_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Kc, eval_ggx(wi, wo, b.Fc, b.Kc_w)));
+  if (b.Kc_w > CRT_FLT_EPS) r = vadd(r, vmul(b.Kc, eval_ggx<OL>(wi, wo, b.Fc, b.Kc_w)));
   return r;
 }
 
@@ -693,9 +706,10 @@ __device__ __forceinline__ float ggx_pdf_term(float hz, float a, float wi_dot_h)
   return ggx_d(hz, a) * fabsf(hz) * 0.25f / wi_dot_h;
 }
 
+template <bool OL = false>
 __device__ __forceinline__ float bsdf_pdf_layered(const Bsdf& b, v3 wo, v3 wi, v3 weight)
 {
-  v3 cf = fresnel_media(wo.z, b.Fc);
+  v3 cf = fresnel_media<OL>(wo.z, b.Fc);
   v3 ct = V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z);
   float pc = dot3(vmul(b.Kc, cf), weight);
   float pd = dot3(vmul(b.Kd, ct), weight);
@@ -727,6 +741,7 @@ __device__ __forceinline__ v3 sample_lambert(v3 wo, v3& wi, float& pdf, uint32_t
   return wo.z >= 0.0f ? V(1, 1, 1) : V(0, 0, 0);
 }
 
+template <bool OL = false>
 __device__ __forceinline__ v3 sample_ggx(v3 wo, v3& wi, v3 fresnel, float a, float& pdf, uint32_t& rng, bool two_sided)
 {
   float k1 = rand_float(rng);
@@ -747,7 +762,7 @@ __device__ __forceinline__ v3 sample_ggx(v3 wo, v3& wi, v3 fresnel, float a, flo
   pdf /= 4.0f * cos_d;
   float g = smith_g1(wo, m, a) * smith_g1(w, m, a);
   if (flip) wi.z = -w.z;
-  return vscale(fresnel_media(cos_d, fresnel), (g * cos_d) / (wo.z * cos_m));
+  return vscale(fresnel_media<OL>(cos_d, fresnel), (g * cos_d) / (wo.z * cos_m));
 }
 
 __device__ __forceinline__ v3 transmitted(float index, v3 wo)
@@ -767,7 +782,7 @@ __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& w
                                                      uint32_t& rng, bool two_sided)
 {
   float pdf = 0.0f;
-  v3 cf = fresnel_media(wo.z, b.Fc);
+  v3 cf = fresnel_media<LEAN>(wo.z, b.Fc);
   v3 ct = V(1.0f - cf.x, 1.0f - cf.y, 1.0f - cf.z);
   float pc = dot3(vmul(b.Kc, cf), weight);
   float pd = dot3(vmul(b.Kd, ct), weight);
@@ -784,7 +799,7 @@ __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& w
       wi = V(-wo.x, -wo.y, wo.z);
       pdf = CRT_MAXFLOAT;
     } else {
-      weight = vmul(weight, sample_ggx(wo, wi, b.Fc, b.Kc_w, pdf, rng, two_sided));
+      weight = vmul(weight, sample_ggx<LEAN>(wo, wi, b.Fc, b.Kc_w, pdf, rng, two_sided));
     }
   } else if (ksi < total) {
     weight = vmul(weight, ct);
@@ -796,11 +811,11 @@ __device__ __forceinline__ float sample_bsdf_layered(const Bsdf& b, v3 wo, v3& w
       pdf = ps / total;
       weight = vmul(weight, vscale(b.Ks, 1.0f / pdf));
       if (b.Ks_w < CRT_FLT_EPS) {
-        weight = vmul(weight, fresnel_media(wo.z, b.Fb));
+        weight = vmul(weight, fresnel_media<LEAN>(wo.z, b.Fb));
         wi = V(-wo.x, -wo.y, wo.z);
         pdf = CRT_MAXFLOAT;
       } else {
-        weight = vmul(weight, sample_ggx(wo, wi, b.Fb, b.Ks_w, pdf, rng, two_sided));
+        weight = vmul(weight, sample_ggx<LEAN>(wo, wi, b.Fb, b.Ks_w, pdf, rng, two_sided));
       }
     } else {
       pdf = pt / total;
@@ -1268,10 +1283,10 @@ __device__ __forceinline__ void shade_bounce(const DeviceScene& S, const DeviceP
       const float dist = sqrtf(dot3(to, to));
       const v3 ldir = sample_light(to, dist, infinite, le_w.w, exp_pdf, rng);
       const v3 wl = to_local(ldir, frame);
-      const float bpdf = bsdf_pdf_layered(B, wo, wl, thr);
+      const float bpdf = bsdf_pdf_layered<LEAN>(B, wo, wl, thr);
       imp_pdf = bpdf;
       const float mis = (exp_pdf == CRT_MAXFLOAT) ? 1.0f : exp_pdf / (exp_pdf * exp_pdf + bpdf * bpdf);
-      const v3 contrib = vscale(vmul(V(le_w.x, le_w.y, le_w.z), eval_bsdf_layered(B, wl, wo, two_sided)), mis);
+      const v3 contrib = vscale(vmul(V(le_w.x, le_w.y, le_w.z), eval_bsdf_layered<LEAN>(B, wl, wo, two_sided)), mis);
       if (any_gt(contrib, CRT_MIN_CONTRIBUTION)) {
         const float side = dot3(ng, ldir) >= 0.0f ? eps : -eps;
         sh_o = vadd(vadd(org, vscale(ldir, eps)), vscale(ng, side));
