@@ -10,10 +10,11 @@
 // (__ballot_sync + __popc, one atomicAdd per warp).  Kernels read the queue length
 // from device memory, so a whole wave is enqueued without a host round trip.
 // Traversal kernels are persistent (grid = SM count x resident CTAs): each lane
-// pulls its next ray from a warp-local pool as soon as its ray finishes
-// (trace_persistent); shading kernels grid-stride with a grid that is a multiple
-// of the SM count.  One wave:
-//   k_generate -> k_extend(0) -> k_shade(0) -> [k_trace_dual(d) -> k_shade(d)]... -> k_connect -> k_resolve
+// pulls its next ray from a warp-local pool when its ray has finished (in batches
+// of finished lanes, trace_persistent); camera rays are walked in lockstep per
+// 8x4 pixel tile; shading kernels grid-stride with a grid that is a multiple
+// of the SM count.  One wave (normally two half-frames of it on two streams):
+//   k_extend_primary_lockstep -> k_shade<FIRST>(0) -> [k_trace_dual(d) -> k_tail(d) -> k_shade(d)]... -> k_connect -> k_resolve
 #pragma once
 #include "device_math.cuh"
 #include "host_scene.hpp"   // kTriStride, reference encodings
@@ -459,9 +460,8 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& S, uint32_t 
     const int n_live = __popc(live);
 #endif
 
-    // ---- inner nodes.  CRT_INNER_EXIT = N > 1: lanes leave the loop once fewer than N lanes are still
-    // walking inner nodes while another lane of the warp waits for its leaf / instance step (the
-    // simulator tests/analysis/simt_model.py predicts fewer issue slots per ray for N around 12).
+    // ---- inner nodes.  Lanes leave the loop once fewer than CRT_INNER_EXIT lanes are still walking inner nodes
+    // while another lane of the warp waits for its leaf / instance step (measurements at the macro's definition).
     while (cur >= 0) {
       if (!QUAD) {
         if (COUNT) { if (any_ray) { cnt.n_inner_any++; cnt.n_boxes_any += 2; } else { cnt.n_inner++; cnt.n_boxes += 2; } }
@@ -1150,7 +1150,7 @@ k_extend_primary(DeviceScene S, PathState st, DeviceParams P, const uint32_t* __
 // (no per-lane refill).  Camera rays of a tile visit nearly the same nodes, so staying in step keeps most lanes active
 // (the persistent driver mixes rays at different stages in a warp: 14.8 of 32 lanes, issue slots 78 % busy).
 #ifndef CRT_PRIMARY_MIN_BLOCKS
-#define CRT_PRIMARY_MIN_BLOCKS 9      // no per-lane refill state: 56 registers without spills (3.13 ms per step at 9 CTAs, 3.25 at 8)
+#define CRT_PRIMARY_MIN_BLOCKS 9      // no per-lane refill state to keep: 56 registers with 20 B of spills (3.13 ms per step at 9 CTAs, 3.25 at 8)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(CRT_TRACE_BLOCK, CRT_PRIMARY_MIN_BLOCKS)
