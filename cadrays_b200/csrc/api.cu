@@ -148,6 +148,7 @@ struct crt_context {
   bool primary_lockstep = true; // camera rays walked in lockstep per 8x4 tile instead of per-lane refill (CRT_PRIMARY_LOCKSTEP=0)
   int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
                                 // 18.90 / 18.80 / 18.57 / 18.45 / 18.43 / 18.47 ms of traversal per step)
+  int sample_group = 16;        // samples of a pixel block that share a warp (1, 4, 8, 16, 32; the largest that divides the wave's sample count is used; CRT_SAMPLE_GROUP)
   bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
   // per-path kernel for the thin end of a wave (k_tail): from bounce `tail_min_depth` on, once at most `tail_max` paths
   // are active, one launch carries them to their end (CRT_TAIL=0 disables, CRT_TAIL_MAX / CRT_TAIL_MIN_DEPTH tune)
@@ -272,6 +273,7 @@ void update_device_params(crt_context* c)
   P.tiles_y = (c->height + 3u) / 4u;
   P.tile0 = 0;
   P.n_tiles = P.tiles_x * P.tiles_y;
+  P.sample_group = 1;
 }
 
 int ensure_path_slots(crt_context* c, uint64_t need)
@@ -635,6 +637,11 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, cons
   Counters* gc = c->d_counters.p;
   const uint32_t n_tiles = c->dp.tiles_x * c->dp.tiles_y;
   const uint64_t paths = (uint64_t)n_tiles * 32u * n_batch;
+  DeviceParams base = c->dp;
+  base.sample_group = 1;
+  if (!adaptive)
+    for (uint32_t G : { 32u, 16u, 8u, 4u })
+      if ((int)G <= c->sample_group && n_batch % G == 0) { base.sample_group = G; break; }
   int parts = 1;
   if (!adaptive && c->side_stream[0] && (c->pipeline == 1 || (c->pipeline == 2 && paths <= c->pipeline_auto_paths && !c->timing_on)))
     parts = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(c->pipeline_parts, (int)crt_context::kMaxParts)), std::max(1u, n_tiles / 64u));
@@ -643,16 +650,16 @@ int launch_batch(crt_context* c, uint32_t n_batch, const uint32_t* d_seeds, cons
   if (parts == 1) {
     const PathState st = make_state(c, 0, 0);
     c->last_parts.push_back({ 0, 0 });
-    enqueue_bounces<COUNT, QUAD>(c, st, c->dp, c->stream, n_batch, d_seeds, adaptive, 0);
+    enqueue_bounces<COUNT, QUAD>(c, st, base, c->stream, n_batch, d_seeds, adaptive, 0);
     SpanGuard g(c, F_RESOLVE);
-    if (adaptive) k_resolve_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, *adaptive, c->accum, COUNT ? gc : nullptr);
-    else k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, c->dp, c->accum, n_batch, COUNT ? gc : nullptr);
+    if (adaptive) k_resolve_adaptive<<<grid_for(c, 8), 256, 0, c->stream>>>(st, base, *adaptive, c->accum, COUNT ? gc : nullptr);
+    else k_resolve<<<grid_for(c, 8), 256, 0, c->stream>>>(st, base, c->accum, n_batch, COUNT ? gc : nullptr);
   } else {
     CRT_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     size_t slot0 = 0;
     for (int k = 0; k < parts; ++k) {
       cudaStream_t s = k == 0 ? c->stream : c->side_stream[k - 1];
-      DeviceParams dp = c->dp;
+      DeviceParams dp = base;
       dp.tile0 = (uint32_t)((uint64_t)n_tiles * k / parts);
       dp.n_tiles = (uint32_t)((uint64_t)n_tiles * (k + 1) / parts) - dp.tile0;
       const PathState st = make_state(c, slot0, k);
@@ -862,6 +869,7 @@ int crt_create(int device_ordinal, crt_context** out)
   if (const char* tv = std::getenv("CRT_PRIMARY_LOCKSTEP")) c->primary_lockstep = std::atoi(tv) != 0;
   if (const char* tv = std::getenv("CRT_PRIMARY_GRID")) c->primary_grid = std::max(1, std::atoi(tv));
   if (const char* tv = std::getenv("CRT_FUSE_PRIMARY")) c->fuse_primary = std::atoi(tv) != 0;
+  if (const char* tv = std::getenv("CRT_SAMPLE_GROUP")) c->sample_group = std::max(1, std::min(32, std::atoi(tv)));
   if (const char* tv = std::getenv("CRT_TAIL")) c->tail = std::atoi(tv) != 0;
   c->tail_max = (uint32_t)c->sm_count * CRT_TAIL_MIN_BLOCKS * 128u;
   if (const char* tv = std::getenv("CRT_TAIL_MAX")) c->tail_max = (uint32_t)std::max(0, std::atoi(tv));

@@ -72,7 +72,58 @@ struct DeviceParams {
   // the part of the frame this launch works on: 8x4 tiles [tile0, tile0 + n_tiles) in row-major tile order (the whole
   // frame unless a wave is split into parts that run on several streams); path slot = sample * n_tiles * 32 + tile * 32 + lane
   uint32_t tile0, n_tiles;
+  // path slot layout of the wave: a warp holds G = sample_group consecutive samples of a block of 32 / G pixels
+  // (G = 1: one sample of an 8x4 pixel tile, slot = k * per_sample + tile * 32 + lane; 4: a 4x2 block; 8: 2x2; 16: 2x1;
+  // 32: one pixel).  Camera rays of one pixel differ by the sub-pixel jitter only, so a warp's rays -- and the bounce
+  // and shadow rays made from them -- start closer together.  Which (pixel, sample) a slot holds never changes a path's
+  // arithmetic; only slot_to_sample / sample_to_slot know the layout.
+  uint32_t sample_group;
 };
+
+// block of pixels a warp covers for G samples per warp: width and height as shifts
+__device__ __forceinline__ void group_block(uint32_t G, uint32_t& bw_s, uint32_t& bh_s)
+{
+  bw_s = G >= 32u ? 0u : (G >= 8u ? 1u : (G >= 4u ? 2u : 3u));     // 8, 4, 2, 2, 1 pixels wide for G = 1, 4, 8, 16, 32
+  bh_s = G >= 16u ? 0u : (G >= 4u ? 1u : 2u);                      // 4, 2, 2, 1, 1 pixels high
+}
+
+__device__ __forceinline__ void slot_to_sample(const DeviceParams& P, uint32_t slot, uint32_t per_sample, uint32_t& px, uint32_t& py, uint32_t& k)
+{
+  const uint32_t G = P.sample_group;
+  if (G > 1u) {
+    uint32_t bw_s, bh_s;
+    group_block(G, bw_s, bh_s);
+    const uint32_t kq = slot / (G * per_sample), in = slot - kq * G * per_sample;
+    const uint32_t tile = P.tile0 + in / (32u * G), w = (in >> 5) % G, l = in & 31u;
+    const uint32_t ppb_s = bw_s + bh_s;                       // log2(pixels per block) = log2(32 / G)
+    const uint32_t pb = l & ((1u << ppb_s) - 1u), ks = l >> ppb_s;
+    const uint32_t cols_s = 3u - bw_s;                        // blocks per tile row = 8 / bw
+    const uint32_t bx = w & ((1u << cols_s) - 1u), by = w >> cols_s;
+    px = (tile % P.tiles_x) * 8u + (bx << bw_s) + (pb & ((1u << bw_s) - 1u));
+    py = (tile / P.tiles_x) * 4u + (by << bh_s) + (pb >> bw_s);
+    k = kq * G + ks;
+  } else {
+    k = slot / per_sample;
+    const uint32_t in = slot - k * per_sample;
+    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
+    px = (tile % P.tiles_x) * 8u + (lane & 7u);
+    py = (tile / P.tiles_x) * 4u + (lane >> 3);
+  }
+}
+
+// slot of sample k of the pixel with tile-order index `in` (tile * 32 + 8x4 lane) of this part of the frame
+__device__ __forceinline__ size_t sample_to_slot(const DeviceParams& P, uint32_t in, uint32_t k, uint32_t per_sample)
+{
+  const uint32_t G = P.sample_group;
+  if (G <= 1u) return (size_t)k * per_sample + in;
+  uint32_t bw_s, bh_s;
+  group_block(G, bw_s, bh_s);
+  const uint32_t lane = in & 31u, lx8 = lane & 7u, ly4 = lane >> 3;
+  const uint32_t bx = lx8 >> bw_s, lx = lx8 & ((1u << bw_s) - 1u), by = ly4 >> bh_s, ly = ly4 & ((1u << bh_s) - 1u);
+  const uint32_t w = (by << (3u - bw_s)) + bx, pb = (ly << bw_s) + lx;
+  const uint32_t l = ((k % G) << (bw_s + bh_s)) + pb;
+  return (size_t)(k / G) * G * per_sample + (size_t)(in >> 5) * 32u * G + w * 32u + l;
+}
 
 struct Counters {   // mirrors crt_stats
   unsigned long long rays_nearest, rays_any, n_inner, n_leaf, n_tri, n_switch, shaded_hits, samples;
@@ -1048,11 +1099,8 @@ k_generate(PathState st, DeviceParams P, const uint32_t* __restrict__ frame_seed
   const bool aligned = (P.width & 7u) == 0 && (P.height & 3u) == 0;
   for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += stride) {
     const uint32_t slot = base + (threadIdx.x & 31u);
-    const uint32_t k = slot / per_sample;
-    const uint32_t in = slot - k * per_sample;
-    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
-    const uint32_t px = (tile % P.tiles_x) * 8u + (lane & 7u);
-    const uint32_t py = (tile / P.tiles_x) * 4u + (lane >> 3);
+    uint32_t px, py, k;
+    slot_to_sample(P, slot, per_sample, px, py, k);
     const bool valid = slot < total && px < P.width && py < P.height;
     if (valid) generate_path(st, P, slot, px, py, __ldg(frame_seeds + k));
     if (aligned) {
@@ -1119,10 +1167,9 @@ struct PrimaryPolicy {
   uint32_t per_sample;
   __device__ __forceinline__ uint32_t load(uint32_t slot, v3& o, v3& d, float& tmax, bool&) const
   {
-    const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
-    uint32_t rng;
-    camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
+    uint32_t px, py, k, rng;
+    slot_to_sample(P, slot, per_sample, px, py, k);
+    camera_ray(P, px, py, __ldg(seeds + k), o, d, rng);
     tmax = CRT_MAXFLOAT;
     return slot;
   }
@@ -1160,11 +1207,11 @@ k_extend_primary_lockstep(DeviceScene S, PathState st, DeviceParams P, const uin
   const uint32_t n = per_sample * n_batch;
   Counters cnt = {};
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-    const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-    const uint32_t tile = P.tile0 + (in >> 5), lane = in & 31u;
+    uint32_t px, py, k;
+    slot_to_sample(P, slot, per_sample, px, py, k);
     v3 o, d;
     uint32_t rng;
-    camera_ray(P, (tile % P.tiles_x) * 8u + (lane & 7u), (tile / P.tiles_x) * 4u + (lane >> 3), __ldg(seeds + k), o, d, rng);
+    camera_ray(P, px, py, __ldg(seeds + k), o, d, rng);
     Hit hit;
     traverse<false, COUNT>(S, o, d, CRT_MAXFLOAT, hit, cnt);
     if (COUNT) cnt.rays_nearest++;
@@ -1474,10 +1521,9 @@ k_shade(DeviceScene S, DeviceParams P, PathState st, int depth, Counters* gcnt, 
       if (FIRST) {
         // depth 0 after k_extend_primary: slot i is pixel sample i; its state is (camera ray, throughput 1, radiance 0)
         slot = i;
-        const uint32_t per_sample = P.n_tiles * 32u;
-        const uint32_t k = slot / per_sample, in = slot - k * per_sample;
-        const uint32_t tile = P.tile0 + (in >> 5), ln = in & 31u;
-        camera_ray(P, (tile % P.tiles_x) * 8u + (ln & 7u), (tile / P.tiles_x) * 4u + (ln >> 3), __ldg(seeds + k), org, dir, rng);
+        uint32_t px, py, k;
+        slot_to_sample(P, slot, P.n_tiles * 32u, px, py, k);
+        camera_ray(P, px, py, __ldg(seeds + k), org, dir, rng);
         thr = V(1.0f, 1.0f, 1.0f);
         hh = ld_stream(&st.hit[slot]);
       } else {
@@ -1678,7 +1724,7 @@ k_resolve(PathState st, DeviceParams P, float4* __restrict__ accum, uint32_t n_b
     if (px >= P.width || py >= P.height) continue;
     float4 a = accum[(size_t)py * P.width + px];
     for (uint32_t k = 0; k < n_batch; ++k) {
-      const float4 c = ld_stream(&st.rad[(size_t)k * per_sample + in]);
+      const float4 c = ld_stream(&st.rad[sample_to_slot(P, in, k, per_sample)]);
       a.x += (c.x != c.x) ? 0.0f : minf(c.x, P.max_radiance);
       a.y += (c.y != c.y) ? 0.0f : minf(c.y, P.max_radiance);
       a.z += (c.z != c.z) ? 0.0f : minf(c.z, P.max_radiance);
