@@ -660,7 +660,7 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
 
 @pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_PRIMARY_LOCKSTEP=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static",
                                   "CRT_PIPELINE=1", "CRT_PIPELINE=0", "CRT_PIPELINE_PARTS=3", "CRT_PIPELINE_PARTS=4", "CRT_SHADE_LEAN=0", "CRT_TAIL=0",
-                                  "CRT_TAIL_MAX=100000000", "CRT_TAIL_MIN_DEPTH=3", "CRT_SHADE_CLASSES=0", "CRT_SMEM_MATS=0"])
+                                  "CRT_TAIL_MAX=100000000", "CRT_TAIL_MIN_DEPTH=3", "CRT_SHADE_CLASSES=0", "CRT_SMEM_MATS=0", "CRT_SAMPLE_GROUP=1"])
 def test_every_kernel_variant_is_bit_equal(knob, monkeypatch, product_lib, oracle_lib):
     """The environment knobs read by crt_create select alternative kernels / launch structures (unsorted shading,
     a separate generate pass, unfused shadow + extend launches, the static traversal loop, the two-stream half-wave
