@@ -261,7 +261,7 @@ def build_roofline(workload, stats, timing, steps, scene_bytes, clocks, probe_de
         "bound": bound, "utilisation_pct": util,
         "bound_note": "`bound` is the unit the ncu counters of the committed launch list (profiles/issue_calibration.json) show nearest "
                       "its limit during the traversal launches: the L1 data pipe (one wavefront per lane and node / triangle / stack "
-                      "access), with issue slots half busy at 16 of 32 lanes; hbm / l2 / issue give every fraction SURVEY 8(d) asks for",
+                      "access), with issue slots half busy at 17 of 32 lanes; hbm / l2 / issue give every fraction SURVEY 8(d) asks for",
         "kernel": "traversal launches: k_extend_primary + k_trace_dual + k_connect (SceneNearestHit / SceneAnyHit)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": traffic, "traffic_provenance": traffic_prov,
