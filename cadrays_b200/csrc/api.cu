@@ -148,7 +148,7 @@ struct crt_context {
   bool primary_lockstep = true; // camera rays walked in lockstep per 8x4 tile instead of per-lane refill (CRT_PRIMARY_LOCKSTEP=0)
   int primary_grid = 72;        // CTAs per SM of the lockstep kernels' grid-stride grid (measured: 9 / 16 / 36 / 72 / 144 / 576 ->
                                 // 18.90 / 18.80 / 18.57 / 18.45 / 18.43 / 18.47 ms of traversal per step)
-  int sample_group = 16;        // samples of a pixel block that share a warp (1, 4, 8, 16, 32; the largest that divides the wave's sample count is used; CRT_SAMPLE_GROUP)
+  int sample_group = 32;        // samples of a pixel block that share a warp (1, 4, 8, 16, 32; the largest that divides the wave's sample count is used; CRT_SAMPLE_GROUP)
   bool fuse_primary = true;     // depth 0 without a generate pass (CRT_FUSE_PRIMARY=0 disables); tile-aligned sizes only
   // per-path kernel for the thin end of a wave (k_tail): from bounce `tail_min_depth` on, once at most `tail_max` paths
   // are active, one launch carries them to their end (CRT_TAIL=0 disables, CRT_TAIL_MAX / CRT_TAIL_MIN_DEPTH tune)

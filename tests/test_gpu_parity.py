@@ -656,6 +656,26 @@ def test_adaptive_sampling_full_size_prefix_property(product_lib):
     view.Remove()
 
 
+def test_slot_layouts_are_bit_equal(monkeypatch, product_lib):
+    """The path-slot layout (how many samples of how small a pixel block share a warp: 1 x 8x4, 4 x 4x2, 8 x 2x2, 16 x 2x1,
+    32 x 1 pixel) only decides which slot holds which (pixel, sample): sums and counts are the same bit for bit, with one
+    wave or two half-frames, for waves of 32, 24 and 5 samples."""
+    def render(group, batch, spp):
+        monkeypatch.setenv("CRT_SAMPLE_GROUP", str(group))
+        d = scenes.materials_scene(320, 192, depth=8, sphere_res=(32, 16))
+        d.params.SamplesPerBatch = batch
+        v = V3d_View(0)
+        d.apply(v)
+        v.Redraw(spp)
+        img = v.BufferDump(Graphic3d_BT_RGB_RayTraceHdrLeft)
+        v.Remove()
+        return img
+    for batch, spp in ((32, 64), (24, 24), (5, 10)):
+        ref = render(1, batch, spp)
+        for group in (4, 8, 16, 32):
+            assert np.array_equal(render(group, batch, spp), ref), (group, batch, spp)
+
+
 # ------------------------------------------------------------------ every A/B knob keeps the result
 
 @pytest.mark.parametrize("knob", ["CRT_SHADE_SORT=0", "CRT_FUSE_PRIMARY=0", "CRT_PRIMARY_LOCKSTEP=0", "CRT_FUSE=0", "CRT_TRAVERSAL=static",
