@@ -299,7 +299,8 @@ uint32_t auto_batch(const crt_context* c)
   if (c->params.samples_per_batch > 0) return (uint32_t)c->params.samples_per_batch;
   const uint64_t px = (uint64_t)c->width * c->height;
   if (!px) return 1;
-  uint64_t b = (16ull << 20) / px;  // about 16 M paths in flight (2.6 GB of path state)
+  uint64_t b = (32ull << 20) / px;  // about 32 M paths in flight (5 GB of path state): 16 samples per wave at 1080p, which also
+                                    // lets a warp hold 16 samples of a pixel pair (sample_group)
   return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b, 64));
 }
 
